@@ -1,0 +1,13 @@
+"""B200-native two-level ADMM for ACOPF — drop-in for the hot path of
+ExaAdmm.jl's ``solve_acopf(...; use_gpu=true)``.
+
+Host side (this package) mirrors the reference's operator API; the compute path
+is the CUDA library behind ``include/exaadmm_b200.h`` (``csrc/``).
+"""
+from .matpower import OPFData, parse_matpower, parse_matpower_text, write_matpower, MatpowerFormatError
+from .grid_data import GridData
+
+__all__ = ["OPFData", "parse_matpower", "parse_matpower_text", "write_matpower",
+           "MatpowerFormatError", "GridData"]
+
+CASE9 = str(__import__("pathlib").Path(__file__).resolve().parent / "data" / "case9.m")

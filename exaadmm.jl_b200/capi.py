@@ -1,0 +1,175 @@
+"""ctypes binding of the C ABI declared in ``include/exaadmm_b200.h``.
+
+This is the Python twin of the Julia ``ccall`` glue in ``julia/`` (the
+reference's host language is Julia, which is not available in the build image;
+see INTEGRATION.md). The shared library is built in-tree by
+``__graft_entry__.build()`` / ``csrc/Makefile``. There is no fallback: if the
+library is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+from .grid_data import GridData
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "csrc" / "_build" / "libexaadmm_b200.so"
+
+EA_OK = 0
+EA_ERR_ARG, EA_ERR_CUDA, EA_ERR_NCCL, EA_ERR_STATE, EA_ERR_ALLOC = -1, -2, -3, -4, -5
+STATUS_NAMES = {0: "NotSpecified", 1: "IterationLimit", 2: "Solved"}
+
+FIELDS = {
+    "u_curr": 0, "v_curr": 1, "l_curr": 2, "rho": 3, "z_curr": 4, "z_prev": 5, "lz": 6,
+    "rp": 7, "rd": 8, "Ax_plus_By": 9,
+    "u_prev": 10, "v_prev": 11, "l_prev": 12, "rp_prev": 13, "z_outer": 14,
+}
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int64)
+
+_GRID_DOUBLE = ("pgmin", "pgmax", "qgmin", "qgmax", "c2", "c1", "c0", "YshR", "YshI",
+                "YffR", "YffI", "YftR", "YftI", "YttR", "YttI", "YtfR", "YtfI",
+                "FrVmBound", "ToVmBound", "FrVaBound", "ToVaBound", "rateA")
+_GRID_INT_A = ("FrStart", "ToStart", "GenStart", "FrIdx", "ToIdx", "GenIdx")
+_GRID_DOUBLE_B = ("Pd", "Qd", "Vmin", "Vmax")
+
+
+class EaGrid(C.Structure):
+    _fields_ = ([("ngen", C.c_int64), ("nline", C.c_int64), ("nbus", C.c_int64), ("baseMVA", C.c_double)]
+                + [(n, _pd) for n in _GRID_DOUBLE]
+                + [(n, _pi) for n in _GRID_INT_A]
+                + [(n, _pd) for n in _GRID_DOUBLE_B]
+                + [("brBusIdx", _pi)])
+
+
+class EaParams(C.Structure):
+    _fields_ = [("mu_max", C.c_double), ("max_auglag", C.c_int32), ("verbose", C.c_int32),
+                ("initial_beta", C.c_double), ("inc_c", C.c_double), ("theta", C.c_double),
+                ("outer_eps", C.c_double), ("MAX_MULTIPLIER", C.c_double), ("scale", C.c_double),
+                ("obj_scale", C.c_double), ("outer_iterlim", C.c_int64), ("inner_iterlim", C.c_int64)]
+
+
+class EaInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("_pad", C.c_int32),
+                ("inner", C.c_int64), ("outer", C.c_int64), ("cumul", C.c_int64),
+                ("objval", C.c_double), ("primres", C.c_double), ("dualres", C.c_double),
+                ("mismatch", C.c_double), ("auglag", C.c_double), ("eps_pri", C.c_double),
+                ("norm_z_curr", C.c_double), ("norm_z_prev", C.c_double), ("beta", C.c_double),
+                ("time_x_update", C.c_double), ("time_xbar_update", C.c_double),
+                ("time_z_update", C.c_double), ("time_l_update", C.c_double),
+                ("time_lz_update", C.c_double), ("time_projection", C.c_double),
+                ("time_overall", C.c_double),
+                ("time_generators", C.c_double), ("time_branches", C.c_double), ("time_buses", C.c_double)]
+
+
+class EaCounters(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("line_calls", "auglag_iters", "tron_evals", "cg_iters",
+                                           "chol_shifts", "rejected_steps", "max_auglag_hits",
+                                           "max_evals_lane")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def make_grid_struct(g: GridData):
+    """Build an ``ea_grid_t`` whose pointers borrow the numpy arrays of ``g``.
+    Returns (struct, keepalive)."""
+    s = EaGrid()
+    keep = []
+    s.ngen, s.nline, s.nbus, s.baseMVA = g.ngen, g.nline, g.nbus, float(g.baseMVA)
+    for n in _GRID_DOUBLE + _GRID_DOUBLE_B:
+        a = np.ascontiguousarray(getattr(g, n), dtype=np.float64)
+        keep.append(a)
+        setattr(s, n, a.ctypes.data_as(_pd))
+    for n in _GRID_INT_A + ("brBusIdx",):
+        a = np.ascontiguousarray(getattr(g, n), dtype=np.int64)
+        keep.append(a)
+        setattr(s, n, a.ctypes.data_as(_pi))
+    return s, keep
+
+
+def params_struct(par) -> EaParams:
+    p = EaParams()
+    for n, _ in EaParams._fields_:
+        setattr(p, n, getattr(par, n))
+    return p
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); must list every symbol include/exaadmm_b200.h declares
+_H = C.c_void_p
+SIGNATURES = {
+    "ea_abi_version": (C.c_int, []),
+    "ea_last_error": (C.c_char_p, [_H]),
+    "ea_device_count": (C.c_int, []),
+    "ea_create": (C.c_int, [C.POINTER(EaGrid), C.c_int, C.POINTER(_H)]),
+    "ea_destroy": (None, [_H]),
+    "ea_init_solution": (C.c_int, [_H, C.c_double, C.c_double]),
+    "ea_outer_prestep": (C.c_int, [_H, _pd]),
+    "ea_inner_prestep": (C.c_int, [_H]),
+    "ea_update_x_gen": (C.c_int, [_H]),
+    "ea_update_x_line": (C.c_int, [_H, C.c_int64, C.c_int32, C.c_double, C.c_double]),
+    "ea_update_x": (C.c_int, [_H, C.c_int64, C.c_int32, C.c_double, C.c_double]),
+    "ea_update_xbar": (C.c_int, [_H]),
+    "ea_update_z": (C.c_int, [_H, C.c_double]),
+    "ea_update_l": (C.c_int, [_H, C.c_double]),
+    "ea_update_residual": (C.c_int, [_H, _pd]),
+    "ea_update_lz": (C.c_int, [_H, C.c_double, C.c_double]),
+    "ea_poststep": (C.c_int, [_H, _pd]),
+    "ea_inner_iteration": (C.c_int, [_H, C.c_int64, C.c_double, C.c_int32, C.c_double, C.c_double, _pd]),
+    "ea_run_inner": (C.c_int, [_H, C.c_int64, C.c_double, C.c_int64, C.c_int32, C.c_double,
+                               C.c_double, C.c_int32, _pi, _pd]),
+    "ea_admm_two_level": (C.c_int, [_H, C.POINTER(EaParams), C.POINTER(EaInfo)]),
+    "ea_nvar": (C.c_int64, [_H]),
+    "ea_get_vector": (C.c_int, [_H, C.c_int, _pd, C.c_int64]),
+    "ea_set_vector": (C.c_int, [_H, C.c_int, _pd, C.c_int64]),
+    "ea_get_membuf": (C.c_int, [_H, C.c_int, _pd, C.c_int64]),
+    "ea_set_membuf": (C.c_int, [_H, C.c_int, _pd, C.c_int64]),
+    "ea_set_load": (C.c_int, [_H, _pd, _pd, C.c_int64]),
+    "ea_set_pg_bounds": (C.c_int, [_H, _pd, _pd, C.c_int64]),
+    "ea_get_counters": (C.c_int, [_H, C.POINTER(EaCounters)]),
+    "ea_reset_counters": (C.c_int, [_H]),
+    "ea_set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
+}
+
+
+def load_library(path: os.PathLike | None = None):
+    """dlopen the in-tree CUDA library and declare every signature."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else Path(os.environ.get("EXAADMM_B200_LIB", LIB_PATH))
+    if not p.exists():
+        raise LibraryMissing(
+            f"{p} not found: the CUDA library is not built. Run `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` (or `make -C {_PKG / 'csrc'}`). There is no CPU fallback on this path.")
+    lib = C.CDLL(str(p))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library drift apart
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ea_abi_version() != 1:
+        raise RuntimeError(f"ABI version mismatch: library {lib.ea_abi_version()}, binding 1")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class EaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"exaadmm_b200 error {code}: {msg}")
+        self.code = code
+
+
+def dptr(a: np.ndarray):
+    return a.ctypes.data_as(_pd)

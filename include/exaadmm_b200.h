@@ -1,0 +1,223 @@
+/*
+ * exaadmm_b200.h — C ABI of the B200-native two-level ADMM ACOPF hot path.
+ *
+ * This is the drop-in boundary for ExaAdmm.jl's operator API on the
+ * `solve_acopf(...; use_gpu=true)` path: every entry point below replaces the
+ * body of one Julia method that the reference dispatches on
+ * (AdmmEnv{T,TD,TI,TM}, AbstractOPFModel{T,TD,TI,TM}) — the citation next to
+ * each declaration is the reference method it stands in for (paths relative to
+ * the reference repository root). A Julia maintainer binds them with `ccall`
+ * (see INTEGRATION.md and exaadmm.jl_b200/julia/); in this repository they are
+ * exercised through Python ctypes (exaadmm.jl_b200/capi.py).
+ *
+ * Conventions
+ *   - plain C types only; all floating point is IEEE binary64;
+ *   - integer index arrays handed in by the caller are int64 and 1-BASED,
+ *     exactly as the Julia side holds them (src/utils/opfdata.jl:613-618);
+ *   - host pointers are borrowed for the duration of the call only; the
+ *     library owns all device memory, streams, events and graphs;
+ *   - vectors cross the boundary in the reference layout
+ *       [ (pg,qg) x ngen | (pij,qij,pji,qji,wi,wj,ti,tj) x nline ]
+ *     (docs/src/dev.md:157-162) regardless of the layout used in HBM;
+ *   - every function returns 0 on success and a negative EA_ERR_* code on
+ *     failure; ea_last_error() gives the message. Nothing throws across the ABI;
+ *   - a handle is single-writer: one host thread at a time. Distinct handles
+ *     are independent;
+ *   - there is NO CPU fallback: without a CUDA device ea_create() fails with
+ *     EA_ERR_CUDA.
+ */
+#ifndef EXAADMM_B200_H
+#define EXAADMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EA_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define EA_OK            0
+#define EA_ERR_ARG      (-1)   /* bad argument (NULL, size mismatch, bad field id) */
+#define EA_ERR_CUDA     (-2)   /* CUDA runtime error (incl. "no device")           */
+#define EA_ERR_NCCL     (-3)   /* NCCL error / NCCL not loadable                    */
+#define EA_ERR_STATE    (-4)   /* call not valid in the current state              */
+#define EA_ERR_ALLOC    (-5)
+
+/* ---- status codes (mod.info.status, src/utils/environment.jl:324)  ------ */
+#define EA_STATUS_NOT_SPECIFIED   0
+#define EA_STATUS_ITERATION_LIMIT 1   /* :IterationLimit, admm_two_level.jl:26 */
+#define EA_STATUS_SOLVED          2   /* :Solved,         admm_two_level.jl:67 */
+
+/* ---- Solution fields (src/utils/environment.jl:177-226) ----------------- */
+enum ea_field {
+    EA_U_CURR = 0, EA_V_CURR = 1, EA_L_CURR = 2, EA_RHO = 3,
+    EA_Z_CURR = 4, EA_Z_PREV = 5, EA_LZ = 6,
+    EA_RP = 7, EA_RD = 8, EA_AX_PLUS_BY = 9,
+    /* allocated-but-unused in the reference's two-level path; kept so that
+       every field of `Solution` can be read back (always zero): */
+    EA_U_PREV = 10, EA_V_PREV = 11, EA_L_PREV = 12, EA_RP_PREV = 13, EA_Z_OUTER = 14,
+    EA_NUM_FIELDS = 15
+};
+
+/* GridData as consumed by the hot path (src/utils/grid_data.jl:61-83,
+ * src/utils/opfdata.jl:542-831). Lengths in comments. */
+typedef struct ea_grid {
+    int64_t ngen, nline, nbus;
+    double  baseMVA;
+    const double *pgmin, *pgmax, *qgmin, *qgmax;      /* ngen, p.u.                       */
+    const double *c2, *c1, *c0;                       /* ngen, UNSCALED       */
+    const double *YshR, *YshI;                        /* nbus                             */
+    const double *YffR, *YffI, *YftR, *YftI;          /* nline                            */
+    const double *YttR, *YttI, *YtfR, *YtfI;          /* nline                            */
+    const double *FrVmBound, *ToVmBound;              /* 2*nline, interleaved (min,max)   */
+    const double *FrVaBound, *ToVaBound;              /* 2*nline                          */
+    const double *rateA;                              /* nline, squared p.u. rating       */
+    const int64_t *FrStart, *ToStart, *GenStart;      /* nbus+1, 1-based CSR pointers     */
+    const int64_t *FrIdx, *ToIdx;                     /* nline, 1-based line ids          */
+    const int64_t *GenIdx;                            /* ngen,  1-based generator ids     */
+    const double *Pd, *Qd;                            /* nbus, MW / MVAr (not p.u.)       */
+    const double *Vmin, *Vmax;                        /* nbus                             */
+    const int64_t *brBusIdx;                          /* 2*nline, 1-based (from,to) bus   */
+} ea_grid_t;
+
+/* The subset of `Parameters` (src/utils/environment.jl:6-76) the hot path reads. */
+typedef struct ea_params {
+    double  mu_max;          /* 1e8   */
+    int32_t max_auglag;      /* 50    */
+    int32_t verbose;         /* 0: silent; >0: per-iteration table like admm_two_level.jl:47-57 */
+    double  initial_beta;    /* 1e3   */
+    double  inc_c;           /* 6.0   */
+    double  theta;           /* 0.8   */
+    double  outer_eps;       /* 2e-4  */
+    double  MAX_MULTIPLIER;  /* 1e12  */
+    double  scale;           /* 1e-4  */
+    double  obj_scale;       /* accepted and stored; inert on this path */
+    int64_t outer_iterlim;   /* 20    */
+    int64_t inner_iterlim;   /* 1000  */
+} ea_params_t;
+
+/* `IterationInformation` + `ComponentInformation` (src/utils/environment.jl:277-358). */
+typedef struct ea_info {
+    int32_t status;
+    int32_t _pad;
+    int64_t inner, outer, cumul;
+    double  objval, primres, dualres, mismatch, auglag, eps_pri;
+    double  norm_z_curr, norm_z_prev;
+    double  beta;                                   /* par.beta after the run */
+    double  time_x_update, time_xbar_update, time_z_update, time_l_update,
+            time_lz_update, time_projection, time_overall;
+    double  time_generators, time_branches, time_buses;
+} ea_info_t;
+
+/* Work counters of the branch kernel, accumulated since the last reset. */
+typedef struct ea_counters {
+    int64_t line_calls;      /* branch sub-problems solved                           */
+    int64_t auglag_iters;    /* augmented-Lagrangian iterations (TRON solves)        */
+    int64_t tron_evals;      /* (f, grad, Hessian) evaluations                       */
+    int64_t cg_iters;        /* projected-CG iterations                              */
+    int64_t chol_shifts;     /* Cholesky factorizations that needed a diagonal shift */
+    int64_t rejected_steps;  /* trust-region steps rejected                          */
+    int64_t max_auglag_hits; /* lines that stopped on max_auglag                     */
+    int64_t max_evals_lane;  /* largest per-line evaluation count seen in one call   */
+} ea_counters_t;
+
+typedef struct ea_handle ea_handle_t;
+
+int  ea_abi_version(void);
+/* Message of the last error on this handle (h may be NULL: last ea_create error). */
+const char *ea_last_error(const ea_handle_t *h);
+/* Number of CUDA devices visible (0 without a GPU; never fails). */
+int  ea_device_count(void);
+
+/* ModelAcopf constructor, device part: GridData H2D copies, Solution and membuf
+ * allocation (src/models/acopf/acopf_model.jl:41-94). Does NOT call
+ * init_solution (call ea_init_solution). `device` = CUDA ordinal (gpu_no). */
+int  ea_create(const ea_grid_t *grid, int device, ea_handle_t **out);
+void ea_destroy(ea_handle_t *h);
+
+/* init_solution! (src/models/acopf/acopf_init_solution_gpu.jl:49-67) + the
+ * membuf reset of acopf_model.jl:87-89. */
+int  ea_init_solution(ea_handle_t *h, double rho_pq, double rho_va);
+
+/* admm_outer_prestep: norm_z_prev = ||z_curr|| (acopf_admm_prepoststep_gpu.jl:1-9). */
+int  ea_outer_prestep(ea_handle_t *h, double *norm_z_prev);
+/* admm_inner_prestep: z_prev <- z_curr (acopf_admm_prepoststep_gpu.jl:11-21). */
+int  ea_inner_prestep(ea_handle_t *h);
+
+/* acopf_admm_update_x_gen -> generator_kernel_two_level
+ * (acopf_admm_update_x_gpu.jl:1-12, acopf_generator_kernel_gpu.jl:1-34). */
+int  ea_update_x_gen(ea_handle_t *h);
+/* acopf_admm_update_x_line -> auglag_linelimit_two_level_alternative + TRON
+ * (acopf_admm_update_x_gpu.jl:14-46, acopf_auglag_linelimit_kernel_gpu.jl:1-151,
+ * acopf_tron_linelimit_kernel.jl:4-149). `inner` is info.inner (mu resets to 10
+ * when it equals 1). */
+int  ea_update_x_line(ea_handle_t *h, int64_t inner, int32_t max_auglag,
+                      double mu_max, double scale);
+/* admm_update_x = gen then line (acopf_admm_update_x_gpu.jl:48-56). */
+int  ea_update_x(ea_handle_t *h, int64_t inner, int32_t max_auglag,
+                 double mu_max, double scale);
+/* admm_update_xbar -> bus_kernel_two_level_alternative
+ * (acopf_admm_update_xbar_gpu.jl:1-13, acopf_bus_kernel_gpu.jl:1-119). */
+int  ea_update_xbar(ea_handle_t *h);
+/* admm_update_z (acopf_admm_update_z_gpu.jl:1-24). */
+int  ea_update_z(ea_handle_t *h, double beta);
+/* admm_update_l (acopf_admm_update_l_gpu.jl:1-26). */
+int  ea_update_l(ea_handle_t *h, double beta);
+/* admm_update_residual (acopf_admm_update_residual_gpu.jl:11-29):
+ * out = { primres, dualres, norm_z_curr, mismatch }. */
+int  ea_update_residual(ea_handle_t *h, double out[4]);
+/* admm_update_lz (acopf_admm_update_lz_gpu.jl:1-20). */
+int  ea_update_lz(ea_handle_t *h, double beta, double max_multiplier);
+/* admm_poststep: objval from the unscaled cost (acopf_admm_prepoststep_gpu.jl:23-42). */
+int  ea_poststep(ea_handle_t *h, double *objval);
+
+/* One whole inner iteration (inner_prestep, update_x, update_xbar, update_z,
+ * update_l, update_residual of admm_two_level.jl:36-42) in two fused launches.
+ * Produces the same iterate as the step-wise calls. */
+int  ea_inner_iteration(ea_handle_t *h, int64_t inner, double beta,
+                        int32_t max_auglag, double mu_max, double scale,
+                        double out[4]);
+
+/* The whole `while inner < inner_iterlim` loop of one outer iteration
+ * (admm_two_level.jl:33-63) with the primres <= eps_pri test evaluated on the
+ * device; the host polls once per `chunk` iterations (chunk <= 0: default).
+ * `outer` is info.outer (eps_pri = sqrt(nvar)/(2500*outer)). On return
+ * *inner_done is info.inner and out = last {primres,dualres,norm_z_curr,mismatch}. */
+int  ea_run_inner(ea_handle_t *h, int64_t outer, double beta,
+                  int64_t inner_iterlim, int32_t max_auglag, double mu_max,
+                  double scale, int32_t chunk, int64_t *inner_done, double out[4]);
+
+/* admm_two_level (src/algorithms/admm_two_level.jl:1-88) end to end, including
+ * admm_poststep. Starts from the current Solution (warm start is implicit, as
+ * in the reference). */
+int  ea_admm_two_level(ea_handle_t *h, const ea_params_t *par, ea_info_t *info);
+
+/* copyto!(host, mod.solution.<field>) / copyto!(mod.solution.<field>, host);
+ * n must equal nvar = 2*ngen + 8*nline. */
+int64_t ea_nvar(const ea_handle_t *h);
+int  ea_get_vector(ea_handle_t *h, int field, double *host, int64_t n);
+int  ea_set_vector(ea_handle_t *h, int field, const double *host, int64_t n);
+/* mod.membuf[row, :] with the reference's 1-based row numbers (acopf_model.jl:87-89):
+ * rows 25,26 = line-limit multipliers, 27 = mu, 29 = rateA are live; rows 1-24 are
+ * re-derived from the Solution on read (they are staging in the reference); set is
+ * accepted for rows 25, 26, 27 and 29. n must equal nline. */
+int  ea_get_membuf(ea_handle_t *h, int row, double *host, int64_t n);
+int  ea_set_membuf(ea_handle_t *h, int row, const double *host, int64_t n);
+
+/* Rolling horizon / scenarios: replace bus loads (acopf_admm_rolling_gpu.jl:42-43)
+ * and the ramp-limited generator bounds (acopf_admm_rolling_gpu.jl:1-14). */
+int  ea_set_load(ea_handle_t *h, const double *Pd, const double *Qd, int64_t nbus);
+int  ea_set_pg_bounds(ea_handle_t *h, const double *pgmin_curr,
+                      const double *pgmax_curr, int64_t ngen);
+
+int  ea_get_counters(ea_handle_t *h, ea_counters_t *out);
+int  ea_reset_counters(ea_handle_t *h);
+/* Enable/disable the work counters (atomics in the branch kernel); default on. */
+int  ea_set_option(ea_handle_t *h, const char *name, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXAADMM_B200_H */
