@@ -129,6 +129,8 @@ SIGNATURES = {
     "ea_inner_iteration": (C.c_int, [_H, C.c_int64, C.c_double, C.c_int32, C.c_double, C.c_double, _pd]),
     "ea_run_inner": (C.c_int, [_H, C.c_int64, C.c_double, C.c_int64, C.c_int32, C.c_double,
                                C.c_double, C.c_int32, _pi, _pd]),
+    "ea_run_inner_from": (C.c_int, [_H, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.c_int32, C.c_double,
+                                    C.c_double, C.c_int32, _pi, _pd]),
     "ea_admm_two_level": (C.c_int, [_H, C.POINTER(EaParams), C.POINTER(EaInfo)]),
     "ea_nvar": (C.c_int64, [_H]),
     "ea_get_vector": (C.c_int, [_H, C.c_int, _pd, C.c_int64]),
@@ -140,6 +142,8 @@ SIGNATURES = {
     "ea_get_counters": (C.c_int, [_H, C.POINTER(EaCounters)]),
     "ea_reset_counters": (C.c_int, [_H]),
     "ea_set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
+    "ea_get_kernel_times": (C.c_int, [_H, _pd]),
+    "ea_diag_branch_eval": (C.c_int, [C.c_int, C.c_int64, _pd, _pd, _pd, C.c_double, _pd, _pd, _pd]),
 }
 
 

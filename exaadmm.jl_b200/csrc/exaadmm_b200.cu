@@ -1,0 +1,749 @@
+// exaadmm_b200.cu — host side of the C ABI (include/exaadmm_b200.h): handle,
+// HBM layout construction, launches, the fused inner loop and the native
+// admm_two_level driver. No torch, no CPU fallback.
+#include "../../include/exaadmm_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+using namespace ea;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Timers { double x = 0, gen = 0, line = 0, bus = 0, z = 0, l = 0, lz = 0; };
+
+}  // namespace
+
+struct ea_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t ngen = 0, nline = 0, nbus = 0, nvar = 0;
+    int nint = 0, gpad = 0;
+    Dev d{};
+    int zsel = 0;                               // host mirror of ctrl->zsel (valid whenever no fused run is in flight)
+    std::vector<void *> allocs;                 // every cudaMalloc, freed in ea_destroy
+    double *fields[EA_NUM_FIELDS] = { nullptr };    // device buffers; Z_CURR / Z_PREV resolved through zsel
+    int *ref2int = nullptr;                     // nvar: HBM index of each reference-layout entry
+    double *staging = nullptr;                  // max(nvar, nline, nbus) doubles (device)
+    double *res_dev = nullptr;                  // 4 doubles (device) for step-wise norms
+    Ctrl *ctrl_host = nullptr;                  // pinned
+    double *res_host = nullptr;                 // pinned, 4 doubles
+    std::vector<int> gen_of_slot;               // generator id (0-based, reference order) per slot
+    std::vector<double> c2, c1, c0;             // reference order, for poststep
+    int max_blocks = 0;
+    branch::PowTable pow_table{};
+    double pow_table_mu_max = -1.0;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    Timers tm;
+    int default_chunk = 16;
+    // launch accounting / optional per-kernel timing of the fused loop
+    double span_s = 0.0;                        // device time spent inside ea_run_inner* calls (events on h->stream)
+    long long n_x = 0, n_bus = 0, n_other = 0;  // kernels launched
+    double t_x = 0.0, t_bus = 0.0;              // summed durations (kernel_timing only)
+    int kernel_timing = 0;
+    std::vector<cudaEvent_t> kev;               // event pool for kernel_timing
+    cudaEvent_t span0 = nullptr, span1 = nullptr;
+    std::string err;
+};
+
+namespace {
+
+int fail(ea_handle *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(h, EA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T> int dev_alloc(ea_handle *h, T **p, size_t n) {
+    void *q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    CK(cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    h->allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return EA_OK;
+}
+template <typename T> int dev_upload(ea_handle *h, T **p, const std::vector<T> &v) {
+    int rc = dev_alloc(h, p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) CK(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return EA_OK;
+}
+
+inline int nblocks(int64_t n, int block) { return (int)std::max<int64_t>(1, (n + block - 1) / block); }
+
+void build_pow_table(ea_handle *h, double mu_max) {
+    if (h->pow_table_mu_max == mu_max) return;
+    branch::PowTable &T = h->pow_table;
+    T.n = 0;
+    double mu = 10.0;                         // acopf_auglag_linelimit_kernel_gpu.jl:75-77
+    for (int k = 0; k < 24; ++k) {
+        T.mu[k] = mu; T.inv_p01[k] = 1.0 / std::pow(mu, 0.1); T.p09[k] = std::pow(mu, 0.9);
+        T.n = k + 1;
+        const double next = std::min(mu_max, mu * 10);
+        if (next == mu) break;
+        mu = next;
+    }
+    h->pow_table_mu_max = mu_max;
+}
+
+double *field_ptr(ea_handle *h, int field) {
+    if (field == EA_Z_CURR) return h->d.zbuf[h->zsel];
+    if (field == EA_Z_PREV) return h->d.zbuf[h->zsel ^ 1];
+    return h->fields[field];
+}
+
+int sync_ctrl_to_device(ea_handle *h, double beta, double eps_pri, long long inner0, long long limit) {
+    k_ctrl_begin<<<1, 1, 0, h->stream>>>(h->d.ctrl, beta, eps_pri, inner0, limit, h->zsel);
+    CK(cudaGetLastError());
+    h->n_other++;
+    return EA_OK;
+}
+
+int launch_x(ea_handle *h, long long major, int zsel, int max_auglag, double mu_max, double scale, int lines, int gens) {
+    build_pow_table(h, mu_max);
+    const int line_blocks = (int)((h->nline + XBLOCK - 1) / XBLOCK);
+    const int gen_blocks = (int)((h->ngen + XBLOCK - 1) / XBLOCK);
+    const int grid = std::max(1, line_blocks + gen_blocks);
+    k_xupdate<<<grid, XBLOCK, 0, h->stream>>>(h->d, h->pow_table, major, zsel, max_auglag, mu_max, scale, lines, gens);
+    CK(cudaGetLastError());
+    h->n_x++;
+    return EA_OK;
+}
+
+double elapsed_s(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return 1e-3 * ms; }
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int ea_abi_version(void) { return EA_ABI_VERSION; }
+
+const char *ea_last_error(const ea_handle_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ea_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
+    ea_handle *h = nullptr;
+    if (!G || !out) return fail(h, EA_ERR_ARG, "ea_create: NULL argument");
+    if (G->ngen < 0 || G->nline < 0 || G->nbus <= 0) return fail(h, EA_ERR_ARG, "ea_create: bad sizes");
+    if (2 * G->ngen + 8 * G->nline > (int64_t)std::numeric_limits<int>::max() / 2)
+        return fail(h, EA_ERR_ARG, "ea_create: problem too large for 32-bit indexing");
+    int ndev = ea_device_count();
+    if (ndev <= 0) return fail(h, EA_ERR_CUDA, "ea_create: no CUDA device available (this path has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(h, EA_ERR_ARG, "ea_create: device %d out of range (0..%d)", device, ndev - 1);
+
+    h = new ea_handle();
+    auto bail = [&](int rc) { g_create_error = h->err; ea_destroy(h); return rc; };
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) return bail(fail(h, EA_ERR_CUDA, "cudaSetDevice(%d) failed", device));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(h, EA_ERR_CUDA, "cudaStreamCreate failed"));
+    for (auto &e : h->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(h, EA_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaEventCreate(&h->span0) != cudaSuccess || cudaEventCreate(&h->span1) != cudaSuccess)
+        return bail(fail(h, EA_ERR_CUDA, "cudaEventCreate failed"));
+
+    const int ngen = (int)G->ngen, nline = (int)G->nline, nbus = (int)G->nbus;
+    h->ngen = ngen; h->nline = nline; h->nbus = nbus; h->nvar = 2 * (int64_t)ngen + 8 * (int64_t)nline;
+    const int gpad = ((2 * ngen + 3) / 4) * 4;
+    const int nint = gpad + 8 * nline;
+    h->gpad = gpad; h->nint = nint;
+
+    // ---- validate and build the bus-sorted layout ----------------------------------
+    std::vector<int> hstart(nbus + 1), gstart(nbus + 1), slot_from(nline, -1), slot_to(nline, -1), slot_of_gen(ngen, -1);
+    h->gen_of_slot.assign(ngen, -1);
+    for (int b = 0; b <= nbus; ++b) {
+        const int64_t fs = G->FrStart[b] - 1, ts = G->ToStart[b] - 1, gs = G->GenStart[b] - 1;
+        if (fs < 0 || fs > nline || ts < 0 || ts > nline || gs < 0 || gs > ngen)
+            return bail(fail(h, EA_ERR_ARG, "ea_create: CSR pointer out of range at bus %d", b));
+        hstart[b] = (int)(fs + ts);
+        gstart[b] = (int)gs;
+    }
+    if (hstart[nbus] != 2 * nline || gstart[nbus] != ngen)
+        return bail(fail(h, EA_ERR_ARG, "ea_create: CSR pointers do not cover all lines/generators"));
+    for (int b = 0; b < nbus; ++b) {
+        int s = hstart[b];
+        for (int64_t k = G->FrStart[b] - 1; k < G->FrStart[b + 1] - 1; ++k, ++s) {
+            const int64_t l = G->FrIdx[k] - 1;
+            if (l < 0 || l >= nline || slot_from[l] >= 0) return bail(fail(h, EA_ERR_ARG, "ea_create: bad FrIdx entry %lld", (long long)k));
+            slot_from[l] = s;
+        }
+        for (int64_t k = G->ToStart[b] - 1; k < G->ToStart[b + 1] - 1; ++k, ++s) {
+            const int64_t l = G->ToIdx[k] - 1;
+            if (l < 0 || l >= nline || slot_to[l] >= 0) return bail(fail(h, EA_ERR_ARG, "ea_create: bad ToIdx entry %lld", (long long)k));
+            slot_to[l] = s;
+        }
+        for (int64_t k = G->GenStart[b] - 1; k < G->GenStart[b + 1] - 1; ++k) {
+            const int64_t g = G->GenIdx[k] - 1;
+            if (g < 0 || g >= ngen || slot_of_gen[g] >= 0) return bail(fail(h, EA_ERR_ARG, "ea_create: bad GenIdx entry %lld", (long long)k));
+            slot_of_gen[g] = (int)k;
+            h->gen_of_slot[k] = (int)g;
+        }
+    }
+    std::vector<int> ref2int((size_t)h->nvar);
+    for (int g = 0; g < ngen; ++g) { ref2int[2 * g] = 2 * slot_of_gen[g]; ref2int[2 * g + 1] = 2 * slot_of_gen[g] + 1; }
+    for (int l = 0; l < nline; ++l) {
+        const size_t base = 2 * (size_t)ngen + 8 * (size_t)l;
+        const int f = gpad + 4 * slot_from[l], t = gpad + 4 * slot_to[l];
+        ref2int[base + 0] = f + 0; ref2int[base + 1] = f + 1; ref2int[base + 2] = t + 0; ref2int[base + 3] = t + 1;
+        ref2int[base + 4] = f + 2; ref2int[base + 5] = t + 2; ref2int[base + 6] = f + 3; ref2int[base + 7] = t + 3;
+    }
+
+    // ---- device allocations -------------------------------------------------------------
+    int rc;
+    Dev &d = h->d;
+    d.ngen = ngen; d.nline = nline; d.nbus = nbus; d.nint = nint; d.gpad = gpad; d.baseMVA = G->baseMVA;
+    for (int f = 0; f < EA_NUM_FIELDS; ++f)
+        if ((rc = dev_alloc(h, &h->fields[f], (size_t)nint))) return bail(rc);
+    d.u = h->fields[EA_U_CURR]; d.v = h->fields[EA_V_CURR]; d.l = h->fields[EA_L_CURR]; d.rho = h->fields[EA_RHO];
+    d.lz = h->fields[EA_LZ]; d.zbuf[0] = h->fields[EA_Z_CURR]; d.zbuf[1] = h->fields[EA_Z_PREV];
+    d.rp = h->fields[EA_RP]; d.rd = h->fields[EA_RD]; d.axby = h->fields[EA_AX_PLUS_BY];
+    h->zsel = 0;
+
+    if ((rc = dev_upload(h, const_cast<int **>(&d.slot_from), slot_from))) return bail(rc);
+    if ((rc = dev_upload(h, const_cast<int **>(&d.slot_to), slot_to))) return bail(rc);
+    if ((rc = dev_upload(h, const_cast<int **>(&d.hstart), hstart))) return bail(rc);
+    if ((rc = dev_upload(h, const_cast<int **>(&d.gstart), gstart))) return bail(rc);
+    if ((rc = dev_upload(h, &h->ref2int, ref2int))) return bail(rc);
+
+    {   // per line
+        std::vector<double> Y(8 * (size_t)nline), xlu(8 * (size_t)nline), rate(nline);
+        std::vector<int> brf(nline), brt(nline);
+        const double *ys[8] = { G->YffR, G->YffI, G->YftR, G->YftI, G->YttR, G->YttI, G->YtfR, G->YtfI };
+        for (int l = 0; l < nline; ++l) {
+            for (int k = 0; k < 8; ++k) Y[(size_t)k * nline + l] = ys[k][l];
+            xlu[(size_t)0 * nline + l] = G->FrVmBound[2 * l]; xlu[(size_t)1 * nline + l] = G->FrVmBound[2 * l + 1];
+            xlu[(size_t)2 * nline + l] = G->ToVmBound[2 * l]; xlu[(size_t)3 * nline + l] = G->ToVmBound[2 * l + 1];
+            xlu[(size_t)4 * nline + l] = G->FrVaBound[2 * l]; xlu[(size_t)5 * nline + l] = G->FrVaBound[2 * l + 1];
+            xlu[(size_t)6 * nline + l] = G->ToVaBound[2 * l]; xlu[(size_t)7 * nline + l] = G->ToVaBound[2 * l + 1];
+            rate[l] = G->rateA[l];
+            const int64_t fb = G->brBusIdx[2 * l] - 1, tb = G->brBusIdx[2 * l + 1] - 1;
+            if (fb < 0 || fb >= nbus || tb < 0 || tb >= nbus) return bail(fail(h, EA_ERR_ARG, "ea_create: bad brBusIdx at line %d", l));
+            brf[l] = (int)fb; brt[l] = (int)tb;
+        }
+        if ((rc = dev_upload(h, const_cast<double **>(&d.Y), Y))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.xlu), xlu))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.rateA), rate))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<int **>(&d.br_from), brf))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<int **>(&d.br_to), brt))) return bail(rc);
+        if ((rc = dev_alloc(h, &d.als, 3 * (size_t)nline))) return bail(rc);       // membuf rows 25-27 start at 0 (acopf_model.jl:87-88)
+    }
+    {   // per generator slot
+        auto permute = [&](const double *src) {
+            std::vector<double> v(ngen);
+            for (int k = 0; k < ngen; ++k) v[k] = src[h->gen_of_slot[k]];
+            return v;
+        };
+        if ((rc = dev_upload(h, const_cast<double **>(&d.pgmin), permute(G->pgmin)))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.pgmax), permute(G->pgmax)))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.pgmin_curr), permute(G->pgmin)))) return bail(rc);   // acopf_model.jl:61-64
+        if ((rc = dev_upload(h, const_cast<double **>(&d.pgmax_curr), permute(G->pgmax)))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.qgmin), permute(G->qgmin)))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.qgmax), permute(G->qgmax)))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.c2), permute(G->c2)))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.c1), permute(G->c1)))) return bail(rc);
+        h->c2.assign(G->c2, G->c2 + ngen); h->c1.assign(G->c1, G->c1 + ngen); h->c0.assign(G->c0, G->c0 + ngen);
+    }
+    {   // per bus
+        std::vector<double> pd(nbus), qd(nbus);
+        for (int b = 0; b < nbus; ++b) { pd[b] = G->Pd[b] / G->baseMVA; qd[b] = G->Qd[b] / G->baseMVA; }   // acopf_bus_kernel_gpu.jl:64-65
+        if ((rc = dev_upload(h, const_cast<double **>(&d.pd_pu), pd))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.qd_pu), qd))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.YshR), std::vector<double>(G->YshR, G->YshR + nbus)))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.YshI), std::vector<double>(G->YshI, G->YshI + nbus)))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.Vmin), std::vector<double>(G->Vmin, G->Vmin + nbus)))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.Vmax), std::vector<double>(G->Vmax, G->Vmax + nbus)))) return bail(rc);
+    }
+    h->max_blocks = std::max(nblocks(nbus, BBLOCK), 1024);
+    if ((rc = dev_alloc(h, &d.partials, 4 * (size_t)h->max_blocks))) return bail(rc);
+    if ((rc = dev_alloc(h, &d.ctrl, 1))) return bail(rc);
+    if ((rc = dev_alloc(h, &d.counters, 1))) return bail(rc);
+    if ((rc = dev_alloc(h, &h->res_dev, 4))) return bail(rc);
+    if ((rc = dev_alloc(h, &h->staging, (size_t)std::max<int64_t>({ h->nvar, (int64_t)nline, (int64_t)nbus, (int64_t)ngen, 1 })))) return bail(rc);
+    d.count_work = 1;
+    if (cudaMallocHost((void **)&h->ctrl_host, sizeof(Ctrl)) != cudaSuccess) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
+    if (cudaMallocHost((void **)&h->res_host, 4 * sizeof(double)) != cudaSuccess) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
+    memset(h->ctrl_host, 0, sizeof(Ctrl));
+    *out = h;
+    return EA_OK;
+}
+
+void ea_destroy(ea_handle_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+    if (h->res_host) cudaFreeHost(h->res_host);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : h->kev) if (e) cudaEventDestroy(e);
+    if (h->span0) cudaEventDestroy(h->span0);
+    if (h->span1) cudaEventDestroy(h->span1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int64_t ea_nvar(const ea_handle_t *h) { return h ? h->nvar : 0; }
+
+int ea_init_solution(ea_handle_t *h, double rho_pq, double rho_va) {
+    if (!h) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    for (int f = 0; f < EA_NUM_FIELDS; ++f) CK(cudaMemsetAsync(h->fields[f], 0, sizeof(double) * (size_t)h->nint, h->stream));
+    h->zsel = 0;
+    const int n = std::max(h->gpad, (int)h->nline);
+    k_init_solution<<<nblocks(n, 128), 128, 0, h->stream>>>(h->d, rho_pq, rho_va);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return EA_OK;
+}
+
+static int norm_of(ea_handle *h, const double *x, double *out) {
+    const int grid = std::min(h->max_blocks, nblocks(h->nint, RBLOCK));
+    k_norm<<<grid, RBLOCK, 0, h->stream>>>(h->nint, x, h->d.partials, &h->d.ctrl->ticket, h->res_dev);
+    CK(cudaGetLastError());
+    h->n_other++;
+    CK(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *out = h->res_host[0];
+    return EA_OK;
+}
+
+int ea_outer_prestep(ea_handle_t *h, double *norm_z_prev) {
+    if (!h || !norm_z_prev) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    return norm_of(h, h->d.zbuf[h->zsel], norm_z_prev);
+}
+
+int ea_inner_prestep(ea_handle_t *h) {
+    if (!h) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d.zbuf[h->zsel ^ 1], h->d.zbuf[h->zsel], sizeof(double) * (size_t)h->nint, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return EA_OK;
+}
+
+static int timed_x(ea_handle *h, int64_t inner, int32_t max_auglag, double mu_max, double scale, int lines, int gens) {
+    if (inner < 1) return fail(h, EA_ERR_ARG, "update_x: info.inner must be >= 1");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    int rc = launch_x(h, inner, h->zsel, max_auglag, mu_max, scale, lines, gens);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const double t = elapsed_s(h->ev[0], h->ev[1]);
+    h->tm.x += t;
+    if (lines) h->tm.line += t; else h->tm.gen += t;
+    return EA_OK;
+}
+
+int ea_update_x_gen(ea_handle_t *h) { return h ? timed_x(h, 1, 1, 1.0, 1.0, 0, 1) : EA_ERR_ARG; }
+
+int ea_update_x_line(ea_handle_t *h, int64_t inner, int32_t max_auglag, double mu_max, double scale) {
+    return h ? timed_x(h, inner, max_auglag, mu_max, scale, 1, 0) : EA_ERR_ARG;
+}
+
+int ea_update_x(ea_handle_t *h, int64_t inner, int32_t max_auglag, double mu_max, double scale) {
+    if (!h) return EA_ERR_ARG;
+    int rc = ea_update_x_gen(h);
+    if (rc) return rc;
+    return ea_update_x_line(h, inner, max_auglag, mu_max, scale);
+}
+
+int ea_update_xbar(ea_handle_t *h) {
+    if (!h) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    k_bus<false><<<nblocks(h->nbus, BBLOCK), BBLOCK, 0, h->stream>>>(h->d, h->zsel, 0.0);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->tm.bus += elapsed_s(h->ev[0], h->ev[1]);
+    return EA_OK;
+}
+
+int ea_update_z(ea_handle_t *h, double beta) {
+    if (!h) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    k_update_z<<<nblocks(h->nint, 256), 256, 0, h->stream>>>(h->nint, h->d.zbuf[h->zsel], h->d.lz, h->d.l, h->d.rho, h->d.u, h->d.v, beta);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->tm.z += elapsed_s(h->ev[0], h->ev[1]);
+    return EA_OK;
+}
+
+int ea_update_l(ea_handle_t *h, double beta) {
+    if (!h) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    k_update_l<<<nblocks(h->nint, 256), 256, 0, h->stream>>>(h->nint, h->d.l, h->d.lz, h->d.zbuf[h->zsel], beta);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->tm.l += elapsed_s(h->ev[0], h->ev[1]);
+    return EA_OK;
+}
+
+int ea_update_lz(ea_handle_t *h, double beta, double max_multiplier) {
+    if (!h) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    k_update_lz<<<nblocks(h->nint, 256), 256, 0, h->stream>>>(h->nint, h->d.lz, h->d.zbuf[h->zsel], beta, max_multiplier);
+    CK(cudaGetLastError());
+    h->n_other++;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->tm.lz += elapsed_s(h->ev[0], h->ev[1]);
+    return EA_OK;
+}
+
+static int residual_vectors(ea_handle *h, double out[4]) {
+    const int grid = std::min(h->max_blocks, nblocks(h->nint, RBLOCK));
+    k_residual<<<grid, RBLOCK, 0, h->stream>>>(h->nint, h->d.u, h->d.v, h->d.zbuf[h->zsel], h->d.zbuf[h->zsel ^ 1],
+                                               h->d.rp, h->d.rd, h->d.axby, h->d.partials, &h->d.ctrl->ticket, h->res_dev);
+    CK(cudaGetLastError());
+    h->n_other++;
+    CK(cudaMemcpyAsync(h->res_host, h->res_dev, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (out) for (int k = 0; k < 4; ++k) out[k] = h->res_host[k];
+    return EA_OK;
+}
+
+int ea_update_residual(ea_handle_t *h, double out[4]) {
+    if (!h || !out) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    return residual_vectors(h, out);
+}
+
+int ea_poststep(ea_handle_t *h, double *objval) {
+    if (!h || !objval) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    std::vector<double> ug((size_t)std::max(h->gpad, 1));
+    CK(cudaMemcpyAsync(ug.data(), h->d.u, sizeof(double) * (size_t)h->gpad, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    // acopf_admm_prepoststep_gpu.jl:35-41: host-side sum over generators in reference order, unscaled cost
+    std::vector<double> pg((size_t)h->ngen);
+    for (int k = 0; k < (int)h->ngen; ++k) pg[h->gen_of_slot[k]] = ug[2 * k];
+    double obj = 0.0;
+    for (int g = 0; g < (int)h->ngen; ++g) {
+        const double p = h->d.baseMVA * pg[g];
+        obj += h->c2[g] * (p * p) + h->c1[g] * p + h->c0[g];
+    }
+    *objval = obj;
+    return EA_OK;
+}
+
+// ---- fused path --------------------------------------------------------------------------
+static int enqueue_iteration(ea_handle *h, int max_auglag, double mu_max, double scale, int slot) {
+    cudaEvent_t *e = nullptr;
+    if (h->kernel_timing) {
+        while ((int)h->kev.size() < 3 * (slot + 1)) {
+            cudaEvent_t ev;
+            CK(cudaEventCreate(&ev));
+            h->kev.push_back(ev);
+        }
+        e = &h->kev[3 * slot];
+        CK(cudaEventRecord(e[0], h->stream));
+    }
+    int rc = launch_x(h, 0, 0, max_auglag, mu_max, scale, 1, 1);
+    if (rc) return rc;
+    if (e) CK(cudaEventRecord(e[1], h->stream));
+    k_bus<true><<<nblocks(h->nbus, BBLOCK), BBLOCK, 0, h->stream>>>(h->d, -1, 0.0);
+    CK(cudaGetLastError());
+    h->n_bus++;
+    if (e) CK(cudaEventRecord(e[2], h->stream));
+    return EA_OK;
+}
+
+static int fetch_ctrl(ea_handle *h) {
+    CK(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->zsel = h->ctrl_host->zsel;
+    return EA_OK;
+}
+
+int ea_inner_iteration(ea_handle_t *h, int64_t inner, double beta, int32_t max_auglag, double mu_max, double scale,
+                       double out[4]) {
+    if (!h || !out) return EA_ERR_ARG;
+    if (inner < 1) return fail(h, EA_ERR_ARG, "ea_inner_iteration: info.inner must be >= 1");
+    CK(cudaSetDevice(h->device));
+    int rc = sync_ctrl_to_device(h, beta, -1.0, inner - 1, std::numeric_limits<long long>::max());
+    if (rc) return rc;
+    const int kt = h->kernel_timing; h->kernel_timing = 0;
+    rc = enqueue_iteration(h, max_auglag, mu_max, scale, 0);
+    h->kernel_timing = kt;
+    if (rc) return rc;
+    if ((rc = fetch_ctrl(h))) return rc;
+    for (int k = 0; k < 4; ++k) out[k] = h->ctrl_host->res[k];
+    return EA_OK;
+}
+
+int ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_start, int64_t inner_limit,
+                      int32_t max_auglag, double mu_max, double scale, int32_t chunk, int64_t *inner_done, double out[4]) {
+    if (!h || !inner_done || !out) return EA_ERR_ARG;
+    if (outer < 1 || inner_start < 0 || inner_limit < inner_start) return fail(h, EA_ERR_ARG, "ea_run_inner: bad outer / inner range");
+    CK(cudaSetDevice(h->device));
+    if (chunk <= 0) chunk = h->default_chunk;
+    const double eps_pri = std::sqrt((double)h->nvar) / (2500.0 * (double)outer);    // admm_two_level.jl:45
+    if (inner_limit == inner_start) { *inner_done = inner_start; for (int k = 0; k < 4; ++k) out[k] = 0.0; return EA_OK; }
+    CK(cudaEventRecord(h->span0, h->stream));
+    int rc = sync_ctrl_to_device(h, beta, eps_pri, inner_start, inner_limit);
+    if (rc) return rc;
+    int64_t enq = inner_start;
+    for (;;) {
+        const int64_t todo = std::min<int64_t>(chunk, inner_limit - enq);
+        for (int64_t i = 0; i < todo; ++i)
+            if ((rc = enqueue_iteration(h, max_auglag, mu_max, scale, (int)i))) return rc;
+        enq += todo;
+        if ((rc = fetch_ctrl(h))) return rc;
+        if (h->kernel_timing) {
+            // iterations that really ran in this chunk (later launches were no-ops)
+            const int64_t ran = std::min<int64_t>(todo, h->ctrl_host->inner - (enq - todo));
+            for (int64_t i = 0; i < ran; ++i) {
+                h->t_x += elapsed_s(h->kev[3 * i], h->kev[3 * i + 1]);
+                h->t_bus += elapsed_s(h->kev[3 * i + 1], h->kev[3 * i + 2]);
+            }
+        }
+        if (h->ctrl_host->done || enq >= inner_limit) break;
+    }
+    *inner_done = h->ctrl_host->inner;
+    for (int k = 0; k < 4; ++k) out[k] = h->ctrl_host->res[k];
+    // leave rp / rd / Ax_plus_By as the reference's last admm_update_residual would
+    rc = residual_vectors(h, nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->span1, h->stream));
+    CK(cudaEventSynchronize(h->span1));
+    h->span_s += elapsed_s(h->span0, h->span1);
+    return EA_OK;
+}
+
+int ea_run_inner(ea_handle_t *h, int64_t outer, double beta, int64_t inner_iterlim, int32_t max_auglag, double mu_max,
+                 double scale, int32_t chunk, int64_t *inner_done, double out[4]) {
+    if (inner_iterlim < 0) return h ? fail(h, EA_ERR_ARG, "ea_run_inner: bad inner_iterlim") : EA_ERR_ARG;
+    return ea_run_inner_from(h, outer, beta, 0, inner_iterlim, max_auglag, mu_max, scale, chunk, inner_done, out);
+}
+
+int ea_get_kernel_times(ea_handle_t *h, double out[8]) {
+    if (!h || !out) return EA_ERR_ARG;
+    out[0] = h->span_s; out[1] = (double)h->n_x; out[2] = h->t_x; out[3] = (double)h->n_bus; out[4] = h->t_bus;
+    out[5] = (double)h->n_other; out[6] = 0.0; out[7] = 0.0;
+    return EA_OK;
+}
+
+int ea_admm_two_level(ea_handle_t *h, const ea_params_t *par, ea_info_t *info) {
+    if (!h || !par || !info) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    const double sqrt_d = std::sqrt((double)h->nvar);
+    const double OUTER_TOL = sqrt_d * par->outer_eps;
+    memset(info, 0, sizeof(*info));
+    info->mismatch = INFINITY; info->norm_z_prev = INFINITY; info->norm_z_curr = INFINITY;
+    double beta = par->initial_beta;
+    double res[4];
+    int rc;
+    if (par->verbose > 0) {     // admm_two_level.jl:15-25
+        if ((rc = ea_update_residual(h, res))) return rc;
+        info->primres = res[0]; info->dualres = res[1]; info->norm_z_curr = res[2]; info->mismatch = res[3];
+        printf("%8s  %8s  %10s  %10s  %10s  %10s  %10s  %10s  %10s  %10s  %10s\n", "Outer", "Inner", "Objval", "AugLag",
+               "PrimRes", "EpsPrimRes", "DualRes", "||z||", "||Ax+By||", "OuterTol", "Beta");
+        printf("%8lld  %8lld  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e\n", 0ll, 0ll, 0.0, 0.0,
+               info->primres, info->eps_pri, info->dualres, info->norm_z_curr, info->mismatch, OUTER_TOL, beta);
+    }
+    info->status = EA_STATUS_ITERATION_LIMIT;
+    h->tm = Timers();
+    const auto t0 = std::chrono::steady_clock::now();
+    while (info->outer < par->outer_iterlim) {
+        info->outer++;
+        if ((rc = ea_outer_prestep(h, &info->norm_z_prev))) return rc;
+        info->inner = 0;
+        if (par->verbose > 0) {
+            // per-iteration table: one host round trip per inner iteration
+            while (info->inner < par->inner_iterlim) {
+                info->inner++; info->cumul++;
+                if ((rc = ea_inner_iteration(h, info->inner, beta, par->max_auglag, par->mu_max, par->scale, res))) return rc;
+                info->primres = res[0]; info->dualres = res[1]; info->norm_z_curr = res[2]; info->mismatch = res[3];
+                info->eps_pri = sqrt_d / (2500.0 * (double)info->outer);
+                if ((info->cumul % 50) == 0)
+                    printf("%8s  %8s  %10s  %10s  %10s  %10s  %10s  %10s  %10s  %10s  %10s\n", "Outer", "Inner", "Objval",
+                           "AugLag", "PrimRes", "EpsPrimRes", "DualRes", "||z||", "||Ax+By||", "OuterTol", "Beta");
+                printf("%8lld  %8lld  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e\n",
+                       (long long)info->outer, (long long)info->inner, info->objval, info->auglag, info->primres,
+                       info->eps_pri, info->dualres, info->norm_z_curr, info->mismatch, OUTER_TOL, beta);
+                if (info->primres <= info->eps_pri) break;
+            }
+            if ((rc = residual_vectors(h, nullptr))) return rc;
+        } else {
+            int64_t done = 0;
+            if ((rc = ea_run_inner(h, info->outer, beta, par->inner_iterlim, par->max_auglag, par->mu_max, par->scale, 0,
+                                   &done, res))) return rc;
+            info->inner = done; info->cumul += done;
+            if (done > 0) { info->primres = res[0]; info->dualres = res[1]; info->norm_z_curr = res[2]; info->mismatch = res[3]; }
+            info->eps_pri = sqrt_d / (2500.0 * (double)info->outer);
+        }
+        if (info->mismatch <= OUTER_TOL) { info->status = EA_STATUS_SOLVED; break; }
+        if ((rc = ea_update_lz(h, beta, par->MAX_MULTIPLIER))) return rc;
+        if (info->norm_z_curr > par->theta * info->norm_z_prev) beta = std::min(par->inc_c * beta, 1e24);
+    }
+    info->time_overall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    info->beta = beta;
+    info->time_x_update = h->tm.x; info->time_xbar_update = h->tm.bus; info->time_z_update = h->tm.z;
+    info->time_l_update = h->tm.l; info->time_lz_update = h->tm.lz;
+    info->time_generators = h->tm.gen; info->time_branches = h->tm.line; info->time_buses = h->tm.bus;
+    return ea_poststep(h, &info->objval);
+}
+
+// ---- data access ----------------------------------------------------------------------------
+int ea_get_vector(ea_handle_t *h, int field, double *host, int64_t n) {
+    if (!h || !host) return EA_ERR_ARG;
+    if (field < 0 || field >= EA_NUM_FIELDS) return fail(h, EA_ERR_ARG, "ea_get_vector: bad field %d", field);
+    if (n != h->nvar) return fail(h, EA_ERR_ARG, "ea_get_vector: n = %lld, expected nvar = %lld", (long long)n, (long long)h->nvar);
+    CK(cudaSetDevice(h->device));
+    if (n == 0) return EA_OK;
+    k_gather<<<nblocks(n, 256), 256, 0, h->stream>>>((int)n, h->ref2int, field_ptr(h, field), h->staging);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, h->staging, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return EA_OK;
+}
+
+int ea_set_vector(ea_handle_t *h, int field, const double *host, int64_t n) {
+    if (!h || !host) return EA_ERR_ARG;
+    if (field < 0 || field >= EA_NUM_FIELDS) return fail(h, EA_ERR_ARG, "ea_set_vector: bad field %d", field);
+    if (n != h->nvar) return fail(h, EA_ERR_ARG, "ea_set_vector: n = %lld, expected nvar = %lld", (long long)n, (long long)h->nvar);
+    CK(cudaSetDevice(h->device));
+    if (n == 0) return EA_OK;
+    CK(cudaMemcpyAsync(h->staging, host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    k_scatter<<<nblocks(n, 256), 256, 0, h->stream>>>((int)n, h->ref2int, h->staging, field_ptr(h, field));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return EA_OK;
+}
+
+int ea_get_membuf(ea_handle_t *h, int row, double *host, int64_t n) {
+    if (!h || !host) return EA_ERR_ARG;
+    if (row < 1 || row > 31) return fail(h, EA_ERR_ARG, "ea_get_membuf: row %d outside 1..31", row);
+    if (n != h->nline) return fail(h, EA_ERR_ARG, "ea_get_membuf: n = %lld, expected nline = %lld", (long long)n, (long long)h->nline);
+    CK(cudaSetDevice(h->device));
+    if (n == 0) return EA_OK;
+    const double *src = nullptr;
+    if (row >= 25 && row <= 27) src = h->d.als + (size_t)(row - 25) * h->nline;
+    else if (row == 29) src = h->d.rateA;
+    else if (row <= 24) {
+        k_membuf_row<<<nblocks(n, 256), 256, 0, h->stream>>>(h->d, h->zsel, row - 1, h->staging);
+        CK(cudaGetLastError());
+        src = h->staging;
+    } else { memset(host, 0, sizeof(double) * (size_t)n); return EA_OK; }
+    CK(cudaMemcpyAsync(host, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return EA_OK;
+}
+
+int ea_set_membuf(ea_handle_t *h, int row, const double *host, int64_t n) {
+    if (!h || !host) return EA_ERR_ARG;
+    if (n != h->nline) return fail(h, EA_ERR_ARG, "ea_set_membuf: n = %lld, expected nline = %lld", (long long)n, (long long)h->nline);
+    CK(cudaSetDevice(h->device));
+    double *dst = nullptr;
+    if (row >= 25 && row <= 27) dst = h->d.als + (size_t)(row - 25) * h->nline;
+    else if (row == 29) dst = const_cast<double *>(h->d.rateA);
+    else return fail(h, EA_ERR_ARG, "ea_set_membuf: only rows 25, 26, 27 and 29 hold state (got %d)", row);
+    if (n == 0) return EA_OK;
+    CK(cudaMemcpyAsync(dst, host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return EA_OK;
+}
+
+int ea_set_load(ea_handle_t *h, const double *Pd, const double *Qd, int64_t nbus) {
+    if (!h || !Pd || !Qd) return EA_ERR_ARG;
+    if (nbus != h->nbus) return fail(h, EA_ERR_ARG, "ea_set_load: nbus = %lld, expected %lld", (long long)nbus, (long long)h->nbus);
+    CK(cudaSetDevice(h->device));
+    std::vector<double> pd((size_t)nbus), qd((size_t)nbus);
+    for (int64_t b = 0; b < nbus; ++b) { pd[b] = Pd[b] / h->d.baseMVA; qd[b] = Qd[b] / h->d.baseMVA; }
+    CK(cudaMemcpy(const_cast<double *>(h->d.pd_pu), pd.data(), sizeof(double) * (size_t)nbus, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<double *>(h->d.qd_pu), qd.data(), sizeof(double) * (size_t)nbus, cudaMemcpyHostToDevice));
+    return EA_OK;
+}
+
+int ea_set_pg_bounds(ea_handle_t *h, const double *lo, const double *hi, int64_t ngen) {
+    if (!h || !lo || !hi) return EA_ERR_ARG;
+    if (ngen != h->ngen) return fail(h, EA_ERR_ARG, "ea_set_pg_bounds: ngen = %lld, expected %lld", (long long)ngen, (long long)h->ngen);
+    CK(cudaSetDevice(h->device));
+    std::vector<double> a((size_t)ngen), b((size_t)ngen);
+    for (int64_t k = 0; k < ngen; ++k) { a[k] = lo[h->gen_of_slot[k]]; b[k] = hi[h->gen_of_slot[k]]; }
+    CK(cudaMemcpy(const_cast<double *>(h->d.pgmin_curr), a.data(), sizeof(double) * (size_t)ngen, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<double *>(h->d.pgmax_curr), b.data(), sizeof(double) * (size_t)ngen, cudaMemcpyHostToDevice));
+    return EA_OK;
+}
+
+int ea_get_counters(ea_handle_t *h, ea_counters_t *out) {
+    if (!h || !out) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    Counters c;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(&c, h->d.counters, sizeof(c), cudaMemcpyDeviceToHost));
+    out->line_calls = (int64_t)c.v[0]; out->auglag_iters = (int64_t)c.v[1]; out->tron_evals = (int64_t)c.v[2];
+    out->cg_iters = (int64_t)c.v[3]; out->chol_shifts = (int64_t)c.v[4]; out->rejected_steps = (int64_t)c.v[5];
+    out->max_auglag_hits = (int64_t)c.v[6]; out->max_evals_lane = (int64_t)c.v[7];
+    return EA_OK;
+}
+
+int ea_reset_counters(ea_handle_t *h) {
+    if (!h) return EA_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemset(h->d.counters, 0, sizeof(Counters)));
+    h->span_s = 0.0; h->n_x = h->n_bus = h->n_other = 0; h->t_x = h->t_bus = 0.0;
+    return EA_OK;
+}
+
+int ea_set_option(ea_handle_t *h, const char *name, double value) {
+    if (!h || !name) return EA_ERR_ARG;
+    if (!strcmp(name, "count_work")) { h->d.count_work = value != 0.0; return EA_OK; }
+    if (!strcmp(name, "chunk")) { h->default_chunk = std::max(1, (int)value); return EA_OK; }
+    if (!strcmp(name, "kernel_timing")) { h->kernel_timing = value != 0.0; return EA_OK; }
+    return fail(h, EA_ERR_ARG, "ea_set_option: unknown option '%s'", name);
+}
+
+int ea_diag_branch_eval(int device, int64_t n, const double *x, const double *param, const double *Y, double scale,
+                        double *f, double *g, double *H) {
+    ea_handle *h = nullptr;
+    if (ea_device_count() <= 0) return fail(h, EA_ERR_CUDA, "ea_diag_branch_eval: no CUDA device");
+    CK(cudaSetDevice(device));
+    double *dx, *dp, *dY, *df, *dg, *dH;
+    CK(cudaMalloc(&dx, 6 * n * sizeof(double))); CK(cudaMalloc(&dp, 31 * n * sizeof(double)));
+    CK(cudaMalloc(&dY, 8 * n * sizeof(double))); CK(cudaMalloc(&df, n * sizeof(double)));
+    CK(cudaMalloc(&dg, 6 * n * sizeof(double))); CK(cudaMalloc(&dH, 36 * n * sizeof(double)));
+    CK(cudaMemcpy(dx, x, 6 * n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dp, param, 31 * n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dY, Y, 8 * n * sizeof(double), cudaMemcpyHostToDevice));
+    k_diag_eval<<<nblocks(n, 128), 128>>>((int)n, dx, dp, dY, scale, df, dg, dH);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(f, df, n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(g, dg, 6 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(H, dH, 36 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dp); cudaFree(dY); cudaFree(df); cudaFree(dg); cudaFree(dH);
+    return EA_OK;
+}
+
+}  // extern "C"

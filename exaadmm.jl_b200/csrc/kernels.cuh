@@ -1,0 +1,513 @@
+// kernels.cuh — device-side data model and the kernels of the ADMM inner loop.
+//
+// HBM layout. Every state vector X (u, v, lambda, rho, z, ...)
+// is ONE array of `nint` doubles:
+//
+//   [ generator part: (pg,qg) per generator, generators sorted by bus, padded to 32 B ]
+//   [ half-line part: 4 doubles (p, q, w, theta) per line END, ends sorted by bus      ]
+//
+// i.e. the reference's 8-entry line record (pij,qij,pji,qji,wi,wj,ti,tj) is split
+// into its from-end (pij,qij,wi,ti) and to-end (pji,qji,wj,tj), each exactly one
+// 32-byte sector, and the ends are stored grouped by the bus they touch. The bus
+// kernel (HBM-bound) then streams contiguous memory; the branch kernel
+// (FP64-bound) does the two 32-byte gathers per vector. The C ABI converts to and
+// from the reference layout with a precomputed index map.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "branch.cuh"
+
+namespace ea {
+
+struct Ctrl {                 // device-resident loop control (one per handle)
+    double res[4];            // primres, dualres, ||z||, ||Ax+By|| of the last finished iteration
+    double beta;
+    double eps_pri;
+    long long inner;          // inner iterations finished in this outer iteration
+    long long inner_limit;
+    int done;                 // 1: primres <= eps_pri or inner == inner_limit; later launches are no-ops
+    int zsel;                 // which of the two z buffers is z_curr
+    unsigned ticket;          // last-block election for the residual reduction
+    int pad;
+};
+
+struct Counters { unsigned long long v[8]; };
+
+struct Dev {                  // everything the kernels need, passed by value
+    int ngen, nline, nbus, nint, gpad;
+    // state (nint each)
+    double *u, *v, *l, *rho, *lz, *zbuf[2], *rp, *rd, *axby;
+    // per line (SoA, nline each)
+    const int *slot_from, *slot_to;       // half-slot index of the from / to end
+    const double *Y;                      // 8 x nline
+    const double *xlu;                    // 8 x nline: xl0,xu0,xl1,xu1,xl2,xu2,xl3,xu3
+    const double *rateA;                  // nline
+    double *als;                          // 3 x nline: lambda_s1, lambda_s2, mu   (membuf rows 25-27)
+    const int *br_from, *br_to;           // bus of each end (init_solution only)
+    // per generator slot (SoA, ngen each)
+    const double *pgmin_curr, *pgmax_curr, *qgmin, *qgmax, *c2, *c1, *pgmin, *pgmax;
+    // per bus
+    const int *hstart, *gstart;           // nbus+1: half-slot / generator-slot CSR
+    const double *pd_pu, *qd_pu, *YshR, *YshI, *Vmin, *Vmax;
+    double baseMVA;
+    // reductions / control
+    double *partials;                     // 4 x max_blocks
+    Ctrl *ctrl;
+    Counters *counters;
+    int count_work;
+};
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+struct __align__(16) d2 { double x, y; };
+struct __align__(32) d4 { double p, q, w, t; };
+
+__device__ __forceinline__ d4 ld4(const double *base, int slot) {
+    const double2 a = *reinterpret_cast<const double2 *>(base + 4 * (size_t)slot);
+    const double2 b = *reinterpret_cast<const double2 *>(base + 4 * (size_t)slot + 2);
+    d4 r; r.p = a.x; r.q = a.y; r.w = b.x; r.t = b.y; return r;
+}
+__device__ __forceinline__ void st4(double *base, int slot, const d4 &v) {
+    *reinterpret_cast<double2 *>(base + 4 * (size_t)slot) = make_double2(v.p, v.q);
+    *reinterpret_cast<double2 *>(base + 4 * (size_t)slot + 2) = make_double2(v.w, v.t);
+}
+
+// z, lambda updates (acopf_admm_update_z_gpu.jl:1-11, acopf_admm_update_l_gpu.jl:1-14)
+__device__ __forceinline__ double z_update(double lz, double l, double rho, double u, double v, double beta) {
+    return (-(lz + l + rho * (u - v))) / (beta + rho);
+}
+__device__ __forceinline__ double l_update(double lz, double beta, double z) { return -(lz + beta * z); }
+
+template <int BLOCK>
+__device__ __forceinline__ void block_sum4(double (&acc)[4], double *smem /* 4*BLOCK/32 */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) smem[k * (BLOCK / 32) + wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < BLOCK / 32; ++w) v += smem[threadIdx.x * (BLOCK / 32) + w];
+        smem[threadIdx.x * (BLOCK / 32)] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = smem[k * (BLOCK / 32)];
+}
+
+// Deterministic grid-wide sum of 4 values: every block stores its partial, the
+// last block to arrive adds them in a fixed order. Returns true in the last block
+// (all threads), with the totals in acc.
+template <int BLOCK>
+__device__ __forceinline__ bool grid_sum4(double (&acc)[4], double *partials, unsigned *ticket, double *smem) {
+    __shared__ bool is_last;
+    block_sum4<BLOCK>(acc, smem);
+    const int nb = gridDim.x;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) partials[k * nb + blockIdx.x] = acc[k];
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == (unsigned)(nb - 1));
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    double a[4] = { 0.0, 0.0, 0.0, 0.0 };
+    for (int b = threadIdx.x; b < nb; b += BLOCK) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] += __ldcg(&partials[k * nb + b]);
+    }
+    __syncthreads();
+    block_sum4<BLOCK>(a, smem);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = a[k];
+    if (threadIdx.x == 0) *ticket = 0u;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// init_solution! (acopf_init_solution_gpu.jl:1-47): generator midpoints, flat-start
+// branch flows, rho_pq / rho_va. All other vectors are zeroed by the host first.
+// ---------------------------------------------------------------------------
+__global__ void k_init_solution(Dev d, double rho_pq, double rho_va) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < d.gpad) d.rho[t] = (t < 2 * d.ngen) ? rho_pq : 0.0;
+    if (t < d.ngen) {
+        d.v[2 * t] = 0.5 * (d.pgmin[t] + d.pgmax[t]);
+        d.v[2 * t + 1] = 0.5 * (d.qgmin[t] + d.qgmax[t]);
+    }
+    if (t < d.nline) {
+        const int fb = d.br_from[t], tb = d.br_to[t];
+        const double wij0 = (d.Vmax[fb] * d.Vmax[fb] + d.Vmin[fb] * d.Vmin[fb]) / 2;
+        const double wji0 = (d.Vmax[tb] * d.Vmax[tb] + d.Vmin[tb] * d.Vmin[tb]) / 2;
+        const double wR0 = sqrt(wij0 * wji0);
+        const double YffR = d.Y[0 * d.nline + t], YffI = d.Y[1 * d.nline + t];
+        const double YftR = d.Y[2 * d.nline + t], YftI = d.Y[3 * d.nline + t];
+        const double YttR = d.Y[4 * d.nline + t], YttI = d.Y[5 * d.nline + t];
+        const double YtfR = d.Y[6 * d.nline + t], YtfI = d.Y[7 * d.nline + t];
+        d4 f, o, r;
+        f.p = YffR * wij0 + YftR * wR0;  f.q = -YffI * wij0 - YftI * wR0;  f.w = wij0;  f.t = 0.0;
+        o.p = YttR * wji0 + YtfR * wR0;  o.q = -YttI * wji0 - YtfI * wR0;  o.w = wji0;  o.t = 0.0;
+        r.p = rho_pq; r.q = rho_pq; r.w = rho_va; r.t = rho_va;
+        double *vh = d.v + d.gpad, *rh = d.rho + d.gpad;
+        st4(vh, d.slot_from[t], f);  st4(vh, d.slot_to[t], o);
+        st4(rh, d.slot_from[t], r);  st4(rh, d.slot_to[t], r);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// x-update: generators (closed form) and branches (AL + TRON), one launch.
+// Replaces generator_kernel_two_level (acopf_generator_kernel_gpu.jl:1-22) and
+// auglag_linelimit_two_level_alternative (acopf_auglag_linelimit_kernel_gpu.jl:1-151).
+//   major_arg > 0 : info.inner supplied by the host (step-wise API)
+//   major_arg == 0: read from the device control block (fused loop)
+// ---------------------------------------------------------------------------
+constexpr int XBLOCK = 128;
+
+__device__ __forceinline__ void generator_update(const Dev &d, const double *z, int k) {
+    const double2 x = *reinterpret_cast<const double2 *>(d.v + 2 * k);
+    const double2 zz = *reinterpret_cast<const double2 *>(z + 2 * k);
+    const double2 l = *reinterpret_cast<const double2 *>(d.l + 2 * k);
+    const double2 rho = *reinterpret_cast<const double2 *>(d.rho + 2 * k);
+    const double B = d.baseMVA;
+    double2 u;
+    u.x = fmax(d.pgmin_curr[k], fmin(d.pgmax_curr[k],
+               (-(d.c1[k] * B + l.x + rho.x * (-x.x + zz.x))) / (2 * d.c2[k] * (B * B) + rho.x)));
+    u.y = fmax(d.qgmin[k], fmin(d.qgmax[k], (-(l.y + rho.y * (-x.y + zz.y))) / rho.y));
+    *reinterpret_cast<double2 *>(d.u + 2 * k) = u;
+}
+
+__global__ void __launch_bounds__(XBLOCK)
+k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_auglag, double mu_max, double scale,
+          int do_lines, int do_gens) {
+    long long major = major_arg;
+    int zsel = zsel_arg;
+    if (major_arg == 0) {
+        if (d.ctrl->done) return;
+        major = d.ctrl->inner + 1;
+        zsel = d.ctrl->zsel;
+    }
+    const double *z = d.zbuf[zsel];
+    const int t = blockIdx.x * XBLOCK + threadIdx.x;
+    const int line_threads = ((d.nline + XBLOCK - 1) / XBLOCK) * XBLOCK;   // generators start on a block boundary
+
+    if (t >= line_threads) {
+        const int k = t - line_threads;
+        if (do_gens && k < d.ngen) generator_update(d, z, k);
+        return;
+    }
+    if (!do_lines) return;
+
+    branch::Work wk;
+    const bool active = t < d.nline;
+    if (active) {
+        const int I = t, nl = d.nline;
+        const int sf = d.slot_from[I], st = d.slot_to[I];
+        const double *uh = d.u + d.gpad, *vh = d.v + d.gpad, *zh = z + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
+        branch::Data D;
+        double x[6], xl[6], xu[6];
+        {
+            const d4 lf = ld4(lh, sf), lt = ld4(lh, st);
+            D.lam[0] = lf.p; D.lam[1] = lf.q; D.lam[2] = lt.p; D.lam[3] = lt.q;
+            D.lam[4] = lf.w; D.lam[5] = lt.w; D.lam[6] = lf.t; D.lam[7] = lt.t;
+            const d4 rf = ld4(rh, sf), rt = ld4(rh, st);
+            D.rho[0] = rf.p; D.rho[1] = rf.q; D.rho[2] = rt.p; D.rho[3] = rt.q;
+            D.rho[4] = rf.w; D.rho[5] = rt.w; D.rho[6] = rf.t; D.rho[7] = rt.t;
+            const d4 vf = ld4(vh, sf), vt = ld4(vh, st), zf = ld4(zh, sf), zt = ld4(zh, st);
+            D.xt[0] = vf.p - zf.p; D.xt[1] = vf.q - zf.q; D.xt[2] = vt.p - zt.p; D.xt[3] = vt.q - zt.q;
+            D.xt[4] = vf.w - zf.w; D.xt[5] = vt.w - zt.w; D.xt[6] = vf.t - zf.t; D.xt[7] = vt.t - zt.t;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) D.Y[k] = d.Y[k * nl + I];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { xl[k] = d.xlu[(2 * k) * nl + I]; xu[k] = d.xlu[(2 * k + 1) * nl + I]; }
+            const double ra = d.rateA[I];
+            xl[4] = -ra; xu[4] = 0.0; xl[5] = -ra; xu[5] = 0.0;
+            // start point from the previous u (auglag_gpu.jl:43-48)
+            const d4 uf = ld4(uh, sf), ut = ld4(uh, st);
+            x[0] = fmin(xu[0], fmax(xl[0], sqrt(uf.w)));
+            x[1] = fmin(xu[1], fmax(xl[1], sqrt(ut.w)));
+            x[2] = fmin(xu[2], fmax(xl[2], uf.t));
+            x[3] = fmin(xu[3], fmax(xl[3], ut.t));
+            x[4] = fmin(xu[4], fmax(xl[4], -(uf.p * uf.p + uf.q * uf.q)));
+            x[5] = fmin(xu[5], fmax(xl[5], -(ut.p * ut.p + ut.q * ut.q)));
+        }
+        branch::Objective obj{ D, { d.als[I], d.als[nl + I] },
+                               (major == 1) ? 10.0 : d.als[2 * nl + I],      // auglag_gpu.jl:75-80
+                               scale };
+        double F[4];
+        branch::solve(obj, xl, xu, x, max_auglag, mu_max, T, F, wk);
+        d4 of, ot;
+        of.p = F[0]; of.q = F[1]; of.w = x[0] * x[0]; of.t = x[2];
+        ot.p = F[2]; ot.q = F[3]; ot.w = x[1] * x[1]; ot.t = x[3];
+        st4(d.u + d.gpad, sf, of);
+        st4(d.u + d.gpad, st, ot);
+        d.als[I] = obj.ls[0]; d.als[nl + I] = obj.ls[1]; d.als[2 * nl + I] = obj.mu;
+    }
+    if (d.count_work) {
+        // per-warp totals -> one atomic per counter per warp
+        unsigned long long vals[7] = { active ? 1ull : 0ull, (unsigned long long)wk.auglag, (unsigned long long)wk.evals,
+                                       (unsigned long long)wk.cg, (unsigned long long)wk.shifts,
+                                       (unsigned long long)wk.rejected, (unsigned long long)wk.hit_max };
+        int mx = wk.evals;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) vals[k] += __shfl_down_sync(0xffffffffu, vals[k], o);
+            mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) if (vals[k]) atomicAdd(&d.counters->v[k], vals[k]);
+            atomicMax(&d.counters->v[7], (unsigned long long)mx);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// bus kernel: xbar (consensus) update; FUSED adds the z and lambda updates, the
+// residual partial sums and, in the last block, the norms + termination test.
+// Replaces bus_kernel_two_level_alternative (acopf_bus_kernel_gpu.jl:1-119) and, when
+// FUSED, update_zv_kernel, update_l_kernel, compute_primal_residual_kernel,
+// vector_difference x2 and the four CUBLAS nrm2 calls
+// (acopf_admm_update_{z,l,residual}_gpu.jl).
+// ---------------------------------------------------------------------------
+constexpr int BBLOCK = 128;
+
+template <bool FUSED>
+__global__ void __launch_bounds__(BBLOCK)
+k_bus(Dev d, int zsel_arg, double beta_arg) {
+    __shared__ double red[4 * (BBLOCK / 32)];
+    int zsel = zsel_arg;
+    double beta = beta_arg;
+    if (FUSED && zsel_arg < 0) {
+        if (d.ctrl->done) return;
+        zsel = d.ctrl->zsel;
+        beta = d.ctrl->beta;
+    }
+    const double *zold = d.zbuf[zsel];
+    double *znew = d.zbuf[zsel ^ 1];
+    const int b = blockIdx.x * BBLOCK + threadIdx.x;
+    double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+    if (b < d.nbus) {
+        const int hs = d.hstart[b], he = d.hstart[b + 1], gs = d.gstart[b], ge = d.gstart[b + 1];
+        const double *uh = d.u + d.gpad, *zh = zold + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
+        double common_wi = 0.0, common_ti = 0.0, inv_p = 0.0, inv_q = 0.0, rs_w = 0.0, rs_t = 0.0;
+        double rhs1 = 0.0, rhs2 = 0.0, inv_pg = 0.0, inv_qg = 0.0;
+        for (int k = gs; k < ge; ++k) {
+            const double2 u = *reinterpret_cast<const double2 *>(d.u + 2 * k);
+            const double2 z = *reinterpret_cast<const double2 *>(zold + 2 * k);
+            const double2 l = *reinterpret_cast<const double2 *>(d.l + 2 * k);
+            const double2 r = *reinterpret_cast<const double2 *>(d.rho + 2 * k);
+            rhs1 += (u.x + z.x) + (l.x / r.x);
+            rhs2 += (u.y + z.y) + (l.y / r.y);
+            inv_pg += 1.0 / r.x;
+            inv_qg += 1.0 / r.y;
+        }
+        rhs1 -= d.pd_pu[b];
+        rhs2 -= d.qd_pu[b];
+        for (int s = hs; s < he; ++s) {
+            const d4 u = ld4(uh, s), z = ld4(zh, s), l = ld4(lh, s), r = ld4(rh, s);
+            common_wi += l.w + r.w * (u.w + z.w);
+            common_ti += l.t + r.t * (u.t + z.t);
+            inv_p += 1.0 / r.p;
+            inv_q += 1.0 / r.q;
+            rs_w += r.w;
+            rs_t += r.t;
+            rhs1 -= (u.p + z.p) + (l.p / r.p);
+            rhs2 -= (u.q + z.q) + (l.q / r.q);
+        }
+        common_wi /= rs_w;
+        const double gr = d.YshR[b], gi = d.YshI[b];
+        rhs1 -= gr * common_wi;
+        rhs2 += gi * common_wi;
+        const double A11 = (inv_pg + inv_p) + (gr * gr / rs_w);
+        const double A12 = -gr * (gi / rs_w);
+        const double A21 = A12;
+        const double A22 = (inv_qg + inv_q) + (gi * gi / rs_w);
+        const double mu2 = (rhs2 - (A21 / A11) * rhs1) / (A22 - (A21 / A11) * A12);
+        const double mu1 = (rhs1 - A12 * mu2) / A11;
+        const double wi = common_wi + ((gr * mu1 - gi * mu2) / rs_w);
+        const double ti = common_ti / rs_t;
+
+        for (int k = gs; k < ge; ++k) {
+            const double2 u = *reinterpret_cast<const double2 *>(d.u + 2 * k);
+            const double2 z = *reinterpret_cast<const double2 *>(zold + 2 * k);
+            const double2 l = *reinterpret_cast<const double2 *>(d.l + 2 * k);
+            const double2 r = *reinterpret_cast<const double2 *>(d.rho + 2 * k);
+            double2 v;
+            v.x = (u.x + z.x) + (l.x - mu1) / r.x;
+            v.y = (u.y + z.y) + (l.y - mu2) / r.y;
+            *reinterpret_cast<double2 *>(d.v + 2 * k) = v;
+            if (FUSED) {
+                const double2 lz = *reinterpret_cast<const double2 *>(d.lz + 2 * k);
+                double2 zn, ln;
+                zn.x = z_update(lz.x, l.x, r.x, u.x, v.x, beta);
+                zn.y = z_update(lz.y, l.y, r.y, u.y, v.y, beta);
+                ln.x = l_update(lz.x, beta, zn.x);
+                ln.y = l_update(lz.y, beta, zn.y);
+                *reinterpret_cast<double2 *>(znew + 2 * k) = zn;
+                *reinterpret_cast<double2 *>(d.l + 2 * k) = ln;
+                const double rpx = u.x - v.x + zn.x, rpy = u.y - v.y + zn.y;
+                const double rdx = zn.x - z.x, rdy = zn.y - z.y;
+                const double abx = rpx - zn.x, aby = rpy - zn.y;
+                acc[0] += rpx * rpx + rpy * rpy;
+                acc[1] += rdx * rdx + rdy * rdy;
+                acc[2] += zn.x * zn.x + zn.y * zn.y;
+                acc[3] += abx * abx + aby * aby;
+            }
+        }
+        for (int s = hs; s < he; ++s) {
+            const d4 u = ld4(uh, s), z = ld4(zh, s), l = ld4(lh, s), r = ld4(rh, s);
+            d4 v;
+            v.p = (u.p + z.p) + (l.p + mu1) / r.p;
+            v.q = (u.q + z.q) + (l.q + mu2) / r.q;
+            v.w = wi;
+            v.t = ti;
+            st4(d.v + d.gpad, s, v);
+            if (FUSED) {
+                const d4 lz = ld4(d.lz + d.gpad, s);
+                d4 zn, ln;
+                zn.p = z_update(lz.p, l.p, r.p, u.p, v.p, beta);
+                zn.q = z_update(lz.q, l.q, r.q, u.q, v.q, beta);
+                zn.w = z_update(lz.w, l.w, r.w, u.w, v.w, beta);
+                zn.t = z_update(lz.t, l.t, r.t, u.t, v.t, beta);
+                ln.p = l_update(lz.p, beta, zn.p);
+                ln.q = l_update(lz.q, beta, zn.q);
+                ln.w = l_update(lz.w, beta, zn.w);
+                ln.t = l_update(lz.t, beta, zn.t);
+                st4(znew + d.gpad, s, zn);
+                st4(d.l + d.gpad, s, ln);
+                const double uu[4] = { u.p, u.q, u.w, u.t }, vv[4] = { v.p, v.q, v.w, v.t };
+                const double zz[4] = { zn.p, zn.q, zn.w, zn.t }, zo[4] = { z.p, z.q, z.w, z.t };
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double rp = uu[k] - vv[k] + zz[k];
+                    const double rd = zz[k] - zo[k];
+                    const double ab = rp - zz[k];
+                    acc[0] += rp * rp; acc[1] += rd * rd; acc[2] += zz[k] * zz[k]; acc[3] += ab * ab;
+                }
+            }
+        }
+    }
+    if (FUSED) {
+        if (grid_sum4<BBLOCK>(acc, d.partials, &d.ctrl->ticket, red) && threadIdx.x == 0) {
+            Ctrl *c = d.ctrl;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c->res[k] = sqrt(acc[k]);
+            const long long inner = c->inner + 1;
+            c->inner = inner;
+            c->zsel = zsel ^ 1;
+            // admm_two_level.jl:60-62 and the `while inner < inner_iterlim` bound (:34)
+            if (c->res[0] <= c->eps_pri || inner >= c->inner_limit) c->done = 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// step-wise element kernels (operator API parity; not on the fused fast path)
+// ---------------------------------------------------------------------------
+__global__ void k_update_z(int n, double *z, const double *lz, const double *l, const double *rho,
+                           const double *u, const double *v, double beta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = z_update(lz[i], l[i], rho[i], u[i], v[i], beta);
+}
+__global__ void k_update_l(int n, double *l, const double *lz, const double *z, double beta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) l[i] = l_update(lz[i], beta, z[i]);
+}
+// acopf_admm_update_lz_gpu.jl:1-12
+__global__ void k_update_lz(int n, double *lz, const double *z, double beta, double M) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lz[i] = fmax(-M, fmin(M, lz[i] + (beta * z[i])));
+}
+
+constexpr int RBLOCK = 256;
+// rp, rd, Ax+By and their norms + ||z|| (acopf_admm_update_residual_gpu.jl:11-29).
+// out[4] receives the four norms (written by the last block).
+__global__ void __launch_bounds__(RBLOCK)
+k_residual(int n, const double *u, const double *v, const double *z, const double *zp,
+           double *rp, double *rd, double *ab, double *partials, unsigned *ticket, double *out) {
+    __shared__ double red[4 * (RBLOCK / 32)];
+    double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+    for (int i = blockIdx.x * RBLOCK + threadIdx.x; i < n; i += gridDim.x * RBLOCK) {
+        const double p = u[i] - v[i] + z[i];
+        const double dd = z[i] - zp[i];
+        const double a = p - z[i];
+        rp[i] = p; rd[i] = dd; ab[i] = a;
+        acc[0] += p * p; acc[1] += dd * dd; acc[2] += z[i] * z[i]; acc[3] += a * a;
+    }
+    if (grid_sum4<RBLOCK>(acc, partials, ticket, red) && threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[k] = sqrt(acc[k]);
+    }
+}
+// ||x||_2 into out[0]
+__global__ void __launch_bounds__(RBLOCK)
+k_norm(int n, const double *x, double *partials, unsigned *ticket, double *out) {
+    __shared__ double red[4 * (RBLOCK / 32)];
+    double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+    for (int i = blockIdx.x * RBLOCK + threadIdx.x; i < n; i += gridDim.x * RBLOCK) acc[0] += x[i] * x[i];
+    if (grid_sum4<RBLOCK>(acc, partials, ticket, red) && threadIdx.x == 0) out[0] = sqrt(acc[0]);
+}
+
+// reference layout <-> HBM layout
+__global__ void k_gather(int n, const int *map, const double *src, double *dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[map[i]];
+}
+__global__ void k_scatter(int n, const int *map, const double *src, double *dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[map[i]] = src[i];
+}
+// membuf rows 1-24 as the reference stages them (auglag_gpu.jl:50-73): row in 0..23
+__global__ void k_membuf_row(Dev d, int zsel, int row, double *out) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= d.nline) return;
+    const int k = row & 7, grp = row >> 3;
+    const bool to_end = (k == 2 || k == 3 || k == 5 || k == 7);
+    const int comp = (k < 2) ? k : (k < 4 ? k - 2 : (k < 6 ? 2 : 3));
+    const size_t idx = (size_t)d.gpad + 4 * (size_t)(to_end ? d.slot_to[I] : d.slot_from[I]) + comp;
+    double val;
+    if (grp == 0) val = d.l[idx];
+    else if (grp == 1) val = d.rho[idx];
+    else val = d.v[idx] - d.zbuf[zsel][idx];
+    out[I] = val;
+}
+
+__global__ void k_ctrl_begin(Ctrl *c, double beta, double eps_pri, long long inner0, long long inner_limit, int zsel) {
+    c->beta = beta; c->eps_pri = eps_pri; c->inner = inner0; c->inner_limit = inner_limit;
+    c->done = 0; c->zsel = zsel; c->ticket = 0u;
+}
+
+// diagnostics: evaluate f, g, H for a batch of points (unit parity vs the oracle)
+__global__ void k_diag_eval(int n, const double *x, const double *param, const double *Y, double scale,
+                            double *f, double *g, double *H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    branch::Data D;
+    double xx[6], ls[2], gg[6], F[4], ff;
+    const double *p = param + 31 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { D.lam[k] = p[k]; D.rho[k] = p[8 + k]; D.xt[k] = p[16 + k]; D.Y[k] = Y[8 * (size_t)i + k]; }
+    ls[0] = p[24]; ls[1] = p[25];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) xx[k] = x[6 * (size_t)i + k];
+    branch::Sym6 A;
+    branch::eval_fgh(D, ls, p[26], scale, xx, ff, gg, A, F);
+    f[i] = ff;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        g[6 * (size_t)i + a] = gg[a];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) H[36 * (size_t)i + 6 * a + b] = A.a[tron::tri(a, b)];
+    }
+}
+
+}  // namespace ea

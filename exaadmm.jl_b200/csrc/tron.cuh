@@ -1,0 +1,439 @@
+// tron.cuh — bound-constrained trust-region Newton (TRON) for tiny dense
+// problems, one problem per thread, everything in registers.
+//
+// Replaces the ExaTron.jl device routines the reference calls from its branch
+// kernel (ExaTron.dtron / dcauchy / dspcg / dtrpcg / dicfs / dprsrch / dgpnorm;
+// call sites /root/reference/src/models/acopf/acopf_tron_linelimit_kernel.jl:103-122).
+// The algorithm is TRON 1.2 (Lin & More', SIOPT 1999) as summarised in
+// SURVEY.md Appendix B. Design differences from the reference's 32-thread-block
+// version:
+//   * N is a template parameter, every loop over variables is fully unrolled and
+//     every vector / the packed symmetric matrix live in registers;
+//   * the free-variable sub-problem of dspcg is not compacted (no indfree
+//     gather): fixed variables are masked, i.e. the reduced matrix is embedded
+//     as diag(1) on the fixed rows. The free block sees exactly the same
+//     operations in the same order (adding exact zeros), so iterates agree with
+//     the compacted form;
+//   * the reverse-communication protocol is flattened into "compute trial step"
+//     and "judge trial step" so that a warp's lanes, each at a different stage
+//     of its own solve, still execute the same code (branch.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+// Device code that can also be compiled for the host: tests/host_harness.cu runs
+// these exact routines on the CPU against the oracle (no GPU needed).
+#ifndef EA_DEV
+#define EA_DEV __host__ __device__ __forceinline__
+#endif
+// EA_NO_FMA (host test harness only) replaces every fused multiply-add by the
+// separately rounded a*b + c, which makes the arithmetic bit-identical to the
+// oracle's (compiled with -ffp-contract=off) so that logic can be compared exactly.
+#ifdef EA_NO_FMA
+#define EA_FMA(a, b, c) ((a) * (b) + (c))
+#else
+#define EA_FMA(a, b, c) fma((a), (b), (c))
+#endif
+
+namespace tron {
+
+__host__ __device__ constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+template <int N> struct Sym { double a[N * (N + 1) / 2]; };   // packed lower triangle
+
+template <int N> EA_DEV double dot(const double (&x)[N], const double (&y)[N]) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) s = EA_FMA(x[i], y[i], s);
+    return s;
+}
+template <int N> EA_DEV double nrm2(const double (&x)[N]) { return sqrt(dot<N>(x, x)); }
+
+// y = A x  (A packed symmetric)
+template <int N> EA_DEV void symv(const Sym<N> &A, const double (&x)[N], double (&y)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) s = EA_FMA(A.a[tri(i, j)], x[j], s);
+        y[i] = s;
+    }
+}
+
+template <int N> EA_DEV void mid(double (&x)[N], const double (&xl)[N], const double (&xu)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = fmax(xl[i], fmin(x[i], xu[i]));
+}
+
+// s = P[x + alpha*w] - x   (Appendix B.1 dgpstep)
+template <int N> EA_DEV void gpstep(const double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                        double alpha, const double (&w)[N], double (&s)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double aw = alpha * w[i];
+        const double xt = x[i] + aw;
+        s[i] = (xt < xl[i]) ? (xl[i] - x[i]) : ((xt > xu[i]) ? (xu[i] - x[i]) : aw);
+    }
+}
+
+// break points along w (B.1 dbreakpt). sgn = +1 uses w, sgn = -1 uses -w.
+template <int N> EA_DEV void breakpt(const double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                         const double (&w)[N], double sgn, double &brptmin, double &brptmax) {
+    bool any = false;
+    brptmin = 0.0; brptmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double wi = sgn * w[i];
+        const bool up = (x[i] < xu[i]) && (wi > 0.0);
+        const bool dn = (x[i] > xl[i]) && (wi < 0.0);
+        if (up || dn) {
+            const double b = ((up ? xu[i] : xl[i]) - x[i]) / wi;
+            brptmin = any ? fmin(brptmin, b) : b;
+            brptmax = any ? fmax(brptmax, b) : b;
+            any = true;
+        }
+    }
+}
+
+// projected gradient sup-norm (B.1 dgpnorm)
+template <int N> EA_DEV double gpnorm(const double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                          const double (&g)[N]) {
+    double nrm = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double v;
+        if (x[i] == xl[i]) v = fabs(fmin(g[i], 0.0));
+        else if (x[i] == xu[i]) v = fabs(fmax(g[i], 0.0));
+        else v = fabs(g[i]);
+        if (xl[i] != xu[i]) nrm = fmax(nrm, v);
+    }
+    return nrm;
+}
+
+// B.1 dtrqsol
+template <int N> EA_DEV double trqsol(const double (&x)[N], const double (&p)[N], double delta) {
+    const double ptx = dot<N>(p, x), ptp = dot<N>(p, p), xtx = dot<N>(x, x);
+    const double dsq = delta * delta;
+    const double rad = sqrt(fmax(EA_FMA(ptx, ptx, ptp * (dsq - xtx)), 0.0));
+    if (ptx > 0.0) return (dsq - xtx) / (ptx + rad);
+    if (rad > 0.0) return (rad - ptx) / ptp;
+    return 0.0;
+}
+
+// q(s) = 0.5 s'As + g's and g's
+template <int N> EA_DEV void quad(const Sym<N> &A, const double (&g)[N], const double (&s)[N],
+                                                      double &q, double &gts) {
+    double w[N];
+    symv<N>(A, s, w);
+    gts = dot<N>(g, s);
+    q = EA_FMA(0.5, dot<N>(s, w), gts);
+}
+
+// Cauchy step (B.2 dcauchy). Returns the new alpha; s is the step.
+template <int N> EA_DEV double cauchy(const double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                          const Sym<N> &A, const double (&g)[N], double delta,
+                                                          double alpha, double (&s)[N]) {
+    const double mu0 = 0.01, interpf = 0.1, extrapf = 10.0;
+    double brptmin, brptmax, q, gts;
+    breakpt<N>(x, xl, xu, g, -1.0, brptmin, brptmax);
+    gpstep<N>(x, xl, xu, -alpha, g, s);
+    bool interp;
+    if (nrm2<N>(s) > delta) interp = true;
+    else { quad<N>(A, g, s, q, gts); interp = (q >= mu0 * gts); }
+    if (interp) {
+        bool search = true;
+#pragma unroll 1
+        while (search) {
+            alpha = interpf * alpha;
+            gpstep<N>(x, xl, xu, -alpha, g, s);
+            if (nrm2<N>(s) <= delta) { quad<N>(A, g, s, q, gts); search = (q > mu0 * gts); }
+        }
+    } else {
+        bool search = true;
+        double alphas = alpha;
+#pragma unroll 1
+        while (search && alpha <= brptmax) {
+            alpha = extrapf * alpha;
+            gpstep<N>(x, xl, xu, -alpha, g, s);
+            if (nrm2<N>(s) <= delta) {
+                quad<N>(A, g, s, q, gts);
+                if (q < mu0 * gts) { search = true; alphas = alpha; }
+            } else search = false;
+        }
+        alpha = alphas;
+        gpstep<N>(x, xl, xu, -alpha, g, s);
+    }
+    return alpha;
+}
+
+// Lower-triangular solves with the free-set mask folded into L (fixed rows are e_i).
+template <int N> EA_DEV void lsolve(const Sym<N> &L, double (&r)[N]) {      // L r = b
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double s = r[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s = EA_FMA(-L.a[tri(i, k)], r[k], s);
+        r[i] = s / L.a[tri(i, i)];
+    }
+}
+template <int N> EA_DEV void ltsolve(const Sym<N> &L, double (&r)[N]) {     // L' r = b
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+        double s = r[i];
+#pragma unroll
+        for (int k = i + 1; k < N; ++k) s = EA_FMA(-L.a[tri(k, i)], r[k], s);
+        r[i] = s / L.a[tri(i, i)];
+    }
+}
+
+// In-place dense Cholesky of the packed lower triangle; false if a pivot is <= 0.
+template <int N> EA_DEV bool cholesky(Sym<N> &L) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double d = L.a[tri(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d = EA_FMA(-L.a[tri(j, k)], L.a[tri(j, k)], d);
+        ok = ok && (d > 0.0);
+        d = sqrt(d);
+        L.a[tri(j, j)] = d;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            double s = L.a[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = EA_FMA(-L.a[tri(i, k)], L.a[tri(j, k)], s);
+            L.a[tri(i, j)] = s / d;
+        }
+    }
+    return ok;
+}
+
+// B.5 dicfs for a dense matrix: scaled Cholesky of the masked matrix with the
+// shift search. Returns true if a diagonal shift was needed.
+template <int N> EA_DEV bool icfs(const Sym<N> &A, unsigned freemask, Sym<N> &L) {
+    const double alpham = 1e-3, nbfactor = 512.0;
+    const int nbmax = 3;
+    double wa2[N];
+    double alphas = alpham, alpha = 0.0;
+    bool needcol = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const bool fr = (freemask >> i) & 1u;
+        const double aii = A.a[tri(i, i)];
+        if (fr && !(aii > 0.0)) needcol = true;
+        wa2[i] = fr ? 1.0 / sqrt(aii) : 1.0;  // aii <= 0 is repaired just below
+    }
+    if (needcol) {                            // rare: non-positive diagonal entry
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool fr = (freemask >> i) & 1u;
+            const double aii = A.a[tri(i, i)];
+            if (fr && !(aii > 0.0)) {
+                double cs = 0.0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const double akj = ((freemask >> k) & 1u) ? A.a[tri(k, i)] : 0.0;
+                    cs = EA_FMA(akj, akj, cs);
+                }
+                wa2[i] = 1.0 / sqrt(sqrt(cs));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if ((freemask >> i) & 1u) {
+            const double aii = A.a[tri(i, i)];
+            if (aii == 0.0) alpha = alphas;
+            else alpha = fmax(alpha, -aii * (wa2[i] * wa2[i]));
+        }
+    }
+    if (alpha > 0.0) alpha = fmax(alpha, alphas);
+    const bool shifted = alpha > 0.0;
+    int nb = 1;
+#pragma unroll 1
+    for (;;) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool fi = (freemask >> i) & 1u;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const bool fj = (freemask >> j) & 1u;
+                double v;
+                if (fi && fj) v = A.a[tri(i, j)] * wa2[i] * wa2[j] + ((i == j) ? alpha : 0.0);
+                else v = (i == j) ? 1.0 : 0.0;
+                L.a[tri(i, j)] = v;
+            }
+        }
+        if (cholesky<N>(L)) {
+            if (alpha == alphas && nb < nbmax) { alphas = alphas / nbfactor; alpha = alphas; nb++; }
+            else {
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) L.a[tri(i, j)] = L.a[tri(i, j)] / wa2[i];
+                break;
+            }
+        } else alpha = fmax(2.0 * alpha, alphas);
+    }
+    return shifted;
+}
+
+// B.4 dtrpcg on the masked system. w is the solution in the L-transformed space.
+template <int N> EA_DEV void trpcg(const Sym<N> &A, unsigned freemask, const double (&g)[N], double delta,
+                                                       const Sym<N> &L, double tol, double stol, int itermax,
+                                                       double (&w)[N], int &iters, int &info) {
+    double t[N], r[N], p[N], q[N], z[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { w[i] = 0.0; t[i] = -g[i]; r[i] = t[i]; }
+    lsolve<N>(L, r);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = r[i];
+    double rho = dot<N>(r, r);
+    if (sqrt(rho) == 0.0) { iters = 0; info = 1; return; }
+    iters = itermax; info = 5;
+#pragma unroll 1
+    for (int it = 1; it <= itermax; ++it) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) z[i] = p[i];
+        ltsolve<N>(L, z);
+        symv<N>(A, z, q);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { q[i] = ((freemask >> i) & 1u) ? q[i] : 0.0; z[i] = q[i]; }
+        lsolve<N>(L, q);
+        const double ptq = dot<N>(p, q);
+        const double alpha = (ptq > 0.0) ? rho / ptq : 0.0;
+        const double sigma = trqsol<N>(w, p, delta);
+        if (ptq <= 0.0 || alpha >= sigma) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) w[i] = EA_FMA(sigma, p[i], w[i]);
+            iters = it; info = (ptq <= 0.0) ? 3 : 4;
+            return;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { w[i] = EA_FMA(alpha, p[i], w[i]); r[i] = EA_FMA(-alpha, q[i], r[i]); t[i] = EA_FMA(-alpha, z[i], t[i]); }
+        const double rtr = dot<N>(r, r);
+        if (nrm2<N>(t) <= tol) { iters = it; info = 1; return; }
+        if (sqrt(rtr) <= stol) { iters = it; info = 2; return; }
+        const double beta = rtr / rho;
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = EA_FMA(beta, p[i], r[i]);
+        rho = rtr;
+    }
+}
+
+// B.6 dprsrch on the masked system (w is zero on fixed variables).
+template <int N> EA_DEV void prsrch(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                        const Sym<N> &A, const double (&g)[N], double (&w)[N]) {
+    const double mu0 = 0.01, interpf = 0.5;
+    double wa1[N], brptmin, brptmax, alpha = 1.0, q, gts;
+    bool search = true;
+    breakpt<N>(x, xl, xu, w, 1.0, brptmin, brptmax);
+#pragma unroll 1
+    while (search && alpha > brptmin) {
+        gpstep<N>(x, xl, xu, alpha, w, wa1);
+        quad<N>(A, g, wa1, q, gts);
+        if (q <= mu0 * gts) search = false;
+        else alpha = interpf * alpha;
+    }
+    if (alpha < 1.0 && alpha < brptmin) alpha = brptmin;
+    gpstep<N>(x, xl, xu, alpha, w, wa1);
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = EA_FMA(alpha, w[i], x[i]);
+    mid<N>(x, xl, xu);
+#pragma unroll
+    for (int i = 0; i < N; ++i) w[i] = wa1[i];
+}
+
+struct Stats { int cg = 0; int shifts = 0; };
+
+// B.3 dspcg: from the Cauchy step s, move x to the trial point; s becomes x_trial - x_0.
+template <int N> EA_DEV void spcg(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                      const Sym<N> &A, const double (&g)[N], double delta, double rtol,
+                                                      double (&s)[N], int itermax, Stats &st) {
+    double w[N];
+    symv<N>(A, s, w);
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] += s[i];
+    mid<N>(x, xl, xu);
+    int iters = 0;
+#pragma unroll 1
+    for (int nfaces = 1; nfaces <= N; ++nfaces) {
+        unsigned freemask = 0;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (xl[j] < x[j] && x[j] < xu[j]) freemask |= (1u << j);
+        if (freemask == 0) return;
+        Sym<N> L;
+        if (icfs<N>(A, freemask, L)) st.shifts++;
+        double gfree[N], wf[N];
+        double gsq = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const bool fr = (freemask >> j) & 1u;
+            gfree[j] = fr ? (w[j] + g[j]) : 0.0;
+            const double gj = fr ? g[j] : 0.0;
+            gsq = EA_FMA(gj, gj, gsq);
+        }
+        const double gfnorm = sqrt(gsq);
+        int itertr, infotr;
+        trpcg<N>(A, freemask, gfree, delta, L, rtol * gfnorm, 0.0, itermax, wf, itertr, infotr);
+        iters += itertr;
+        st.cg += itertr;
+        ltsolve<N>(L, wf);
+        prsrch<N>(x, xl, xu, A, gfree, wf);
+#pragma unroll
+        for (int j = 0; j < N; ++j) s[j] += wf[j];
+        symv<N>(A, s, w);
+        double gf2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const double v = ((freemask >> j) & 1u) ? (w[j] + g[j]) : 0.0;
+            gf2 = EA_FMA(v, v, gf2);
+        }
+        if (sqrt(gf2) <= rtol * gfnorm) return;
+        if (infotr == 3 || infotr == 4) return;
+        if (iters > itermax) return;
+    }
+}
+
+// One "COMPUTE" of dtron (B.0): Cauchy point + projected CG. On entry x is the
+// current iterate; on exit x is the trial point, prered the predicted reduction,
+// gts = g's and snorm = |s| for the step s = trial - x_c.
+template <int N> EA_DEV void compute_step(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                              const Sym<N> &A, const double (&g)[N], double delta,
+                                                              double &alphac, double &prered, double &gts, double &snorm,
+                                                              Stats &st) {
+    const double cgtol = 0.1;
+    double s[N];
+    alphac = cauchy<N>(x, xl, xu, A, g, delta, alphac, s);
+    spcg<N>(x, xl, xu, A, g, delta, cgtol, s, N, st);
+    double q;
+    quad<N>(A, g, s, q, gts);
+    prered = -q;
+    snorm = nrm2<N>(s);
+}
+
+// The "EVALUATE" part of dtron (B.0): trust-region update and acceptance.
+// Returns: 0 = rejected (task F), 1 = accepted (task GH), 2 = converged/warn.
+EA_DEV int judge_step(double f_trial, double fc, double g0, double snorm, double prered,
+                                          bool first_iter, double &delta, bool &accepted) {
+    const double eta0 = 1e-4, eta1 = 0.25, eta2 = 0.75, sigma1 = 0.25, sigma2 = 0.5, sigma3 = 4.0;
+    const double frtol = 1e-12, fatol = 0.0, fmin_ = -1e32;
+    const double actred = fc - f_trial;
+    if (first_iter) delta = fmin(delta, snorm);
+    const double den = f_trial - fc - g0;
+    const double alpha = (den <= 0.0) ? sigma3 : fmax(sigma1, -0.5 * (g0 / den));
+    if (actred < eta0 * prered) delta = fmin(fmax(alpha, sigma1) * snorm, sigma2 * delta);
+    else if (actred < eta1 * prered) delta = fmax(sigma1 * delta, fmin(alpha * snorm, sigma2 * delta));
+    else if (actred < eta2 * prered) delta = fmax(sigma1 * delta, fmin(alpha * snorm, sigma3 * delta));
+    else delta = fmax(delta, fmin(alpha * snorm, sigma3 * delta));
+    accepted = actred > eta0 * prered;
+    const double f = accepted ? f_trial : fc;
+    int task = accepted ? 1 : 0;
+    if (f < fmin_) task = 2;
+    if (fabs(actred) <= fatol && prered <= fatol) task = 2;
+    if (fabs(actred) <= frtol * fabs(f) && prered <= frtol * fabs(f)) task = 2;
+    return task;
+}
+
+}  // namespace tron

@@ -137,8 +137,9 @@ int  ea_device_count(void);
 int  ea_create(const ea_grid_t *grid, int device, ea_handle_t **out);
 void ea_destroy(ea_handle_t *h);
 
-/* init_solution! (src/models/acopf/acopf_init_solution_gpu.jl:49-67) + the
- * membuf reset of acopf_model.jl:87-89. */
+/* init_solution! (src/models/acopf/acopf_init_solution_gpu.jl:49-67). As in the
+ * reference, membuf (rows 25-27: line-limit multipliers and mu) is zeroed once by
+ * the constructor (ea_create, acopf_model.jl:87-89) and is NOT reset here. */
 int  ea_init_solution(ea_handle_t *h, double rho_pq, double rho_va);
 
 /* admm_outer_prestep: norm_z_prev = ||z_curr|| (acopf_admm_prepoststep_gpu.jl:1-9). */
@@ -189,6 +190,12 @@ int  ea_run_inner(ea_handle_t *h, int64_t outer, double beta,
                   int64_t inner_iterlim, int32_t max_auglag, double mu_max,
                   double scale, int32_t chunk, int64_t *inner_done, double out[4]);
 
+/* Same loop, resumable: counts inner iterations from `inner_start` (so that the mu reset
+ * keyed on info.inner == 1 fires only at the true start) up to `inner_limit`. */
+int  ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_start,
+                       int64_t inner_limit, int32_t max_auglag, double mu_max, double scale,
+                       int32_t chunk, int64_t *inner_done, double out[4]);
+
 /* admm_two_level (src/algorithms/admm_two_level.jl:1-88) end to end, including
  * admm_poststep. Starts from the current Solution (warm start is implicit, as
  * in the reference). */
@@ -214,8 +221,19 @@ int  ea_set_pg_bounds(ea_handle_t *h, const double *pgmin_curr,
 
 int  ea_get_counters(ea_handle_t *h, ea_counters_t *out);
 int  ea_reset_counters(ea_handle_t *h);
-/* Enable/disable the work counters (atomics in the branch kernel); default on. */
+/* Options: "count_work" (0/1, atomics for ea_counters_t in the branch kernel, default 1),
+ * "chunk" (inner iterations enqueued per host poll in ea_run_inner*, default 16),
+ * "kernel_timing" (0/1, bracket every kernel of the fused loop with CUDA events). */
 int  ea_set_option(ea_handle_t *h, const char *name, double value);
+/* Launch accounting since the last ea_reset_counters: out = { device seconds spent in
+ * ea_run_inner* (events on the library's stream), x-update launches, their summed
+ * duration [s] (kernel_timing only), bus-kernel launches, their summed duration [s],
+ * other launches, 0, 0 }. Feeds info.time_* and bench.py (print_statistics.jl:12-19). */
+int  ea_get_kernel_times(ea_handle_t *h, double out[8]);
+/* Diagnostics: f, gradient (6) and Hessian (6x6 row-major) of the branch objective for
+ * n points on the device; param = 31 doubles per point (one membuf column), Y = 8. */
+int  ea_diag_branch_eval(int device, int64_t n, const double *x, const double *param,
+                         const double *Y, double scale, double *f, double *g, double *H);
 
 #ifdef __cplusplus
 }

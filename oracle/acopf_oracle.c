@@ -615,9 +615,8 @@ void orc_init_solution(orc_model_t *m, double rho_pq, double rho_va) {
         p[4] = wij0; p[5] = wji0; p[6] = 0.0; p[7] = 0.0;
         for (int k = 4; k < 8; ++k) rho[ls + 8 * l + k] = rho_va;
     }
-    /* acopf_model.jl:87-89 (fresh model): membuf = 0, row 29 = rateA */
-    memset(m->membuf, 0, sizeof(double) * (size_t)(MEMROWS * m->nline));
-    for (int64_t l = 0; l < m->nline; ++l) m->membuf[l * MEMROWS + 28] = m->rateA[l];
+    /* membuf is NOT touched here: it is zeroed once by the model constructor
+     * (acopf_model.jl:87-89 -> orc_create) and persists across init_solution! calls. */
 }
 
 /* acopf_admm_prepoststep_cpu.jl:1-10 */
@@ -711,11 +710,11 @@ static void solve_branch(orc_model_t *m, int64_t I, int64_t major_iter, int32_t 
     param[26] = mu;
     cnt->line_calls++;
     cnt->auglag_iters += it;
-    cnt->tron_evals += st.ngev;
+    cnt->tron_evals += st.nfev;   /* 1 at the start point + 1 per trial point */
     cnt->cg_iters += st.cg;
     cnt->chol_shifts += st.shifts;
     cnt->rejected_steps += st.rejected;
-    if (st.ngev > cnt->max_evals_lane) cnt->max_evals_lane = st.ngev;
+    if (st.nfev > cnt->max_evals_lane) cnt->max_evals_lane = st.nfev;
 }
 
 static void merge_counters(ea_counters_t *dst, const ea_counters_t *src) {

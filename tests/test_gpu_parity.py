@@ -1,0 +1,239 @@
+"""CUDA path vs oracle / reference goldens, through the C ABI (run on the B200 box).
+Mirrors test/algorithms/acopf_update_gpu.jl:1-194: operator-level known answers,
+then the end-to-end solve; plus per-iterate comparisons against the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+import exaadmm_b200 as ea
+from exaadmm_b200 import operators as ops
+from exaadmm_b200.admm_two_level import admm_two_level
+from exaadmm_b200.environment import AdmmEnv, Parameters
+from exaadmm_b200.model import ModelAcopf
+from exaadmm_b200.solve_acopf import solve_acopf
+from exaadmm_b200.synthetic import synthetic_case
+from oracle.oracle import OracleModel
+
+pytestmark = pytest.mark.gpu
+
+ITERATE_TOL = 1e-8          # north-star: per-iterate max-abs difference <= 1e-8 (fp64)
+
+
+def _env_mod(case, rho_pq=4e2, rho_va=4e4, **kw):
+    env = AdmmEnv(case, rho_pq, rho_va, use_gpu=True, verbose=0, **kw)
+    mod = ModelAcopf(env)
+    return env, mod
+
+
+def test_operator_level_goldens_case9(golden):
+    atol = golden["atol"]
+    env, mod = _env_mod(ea.CASE9)
+    sol = mod.solution
+    env.params.scale = 1e-4; env.params.initial_beta = 1e3; env.params.beta = 1e3
+    ops.admm_increment_outer(env, mod); ops.admm_outer_prestep(env, mod)
+    ops.admm_increment_reset_inner(env, mod); ops.admm_increment_inner(env, mod); ops.admm_inner_prestep(env, mod)
+    ops.admm_update_x(env, mod)
+    u = sol.u_curr
+    np.testing.assert_allclose(u[:6], golden["U_GEN"], atol=atol, rtol=0)
+    np.testing.assert_allclose(u[6:], golden["U_BR"], atol=atol, rtol=0)
+    ops.admm_update_xbar(env, mod)
+    v = sol.v_curr
+    np.testing.assert_allclose(v[:6], golden["V_GEN"], atol=atol, rtol=0)
+    np.testing.assert_allclose(v[6:], golden["V_BR"], atol=atol, rtol=0)
+    ops.admm_update_z(env, mod)
+    z = sol.z_curr
+    np.testing.assert_allclose(z[:6], golden["Z_GEN"], atol=atol, rtol=0)
+    np.testing.assert_allclose(z[6:], golden["Z_BR"], atol=atol, rtol=0)
+    ops.admm_update_l(env, mod)
+    l = sol.l_curr
+    np.testing.assert_allclose(l[:6], golden["L_GEN"], atol=atol, rtol=0)
+    np.testing.assert_allclose(l[6:], golden["L_BR"], atol=atol, rtol=0)
+    ops.admm_update_residual(env, mod)
+    np.testing.assert_allclose(sol.rp, u - v + z, atol=atol)
+    np.testing.assert_allclose(sol.rd, z - sol.z_prev, atol=atol)
+    np.testing.assert_allclose(sol.Ax_plus_By, u - v, atol=atol)
+    assert mod.info.primres == pytest.approx(np.linalg.norm(u - v + z), rel=1e-13)
+    assert mod.info.mismatch == pytest.approx(np.linalg.norm(u - v), rel=1e-13)
+    lz_prev = sol.lz
+    ops.admm_update_lz(env, mod)
+    np.testing.assert_allclose(sol.lz, lz_prev + env.params.beta * z, atol=atol)
+    mod.close()
+
+
+@pytest.mark.parametrize("mode", ["stepwise", "fused", "native"])
+def test_case9_solve_known_answer(golden, mode):
+    pin = golden["solve_case9"]
+    env, mod = solve_acopf(ea.CASE9, use_gpu=True, verbose=0, mode=mode, **pin["kwargs"])
+    assert mod.info.status == "Solved"
+    assert mod.info.outer == pin["outer"]
+    assert mod.info.cumul == pin["cumul"]
+    assert abs(mod.info.objval - pin["objval"]) <= pin["objval_atol"]
+    mod.close()
+
+
+def test_case9_solve_matches_oracle_to_1e6_relative(case9_grid):
+    par = Parameters(); par.verbose = 0; par.outer_iterlim = 25; par.outer_eps = 2e-5
+    om = OracleModel(case9_grid, par, 4e2, 4e4)
+    oinfo = om.admm_two_level()
+    env, mod = solve_acopf(ea.CASE9, use_gpu=True, verbose=0, outer_iterlim=25, outer_eps=2e-5)
+    assert (mod.info.outer, mod.info.cumul) == (oinfo.outer, oinfo.cumul)
+    assert abs(mod.info.objval - oinfo.objval) <= 1e-6 * abs(oinfo.objval)
+    assert mod.info.primres == pytest.approx(oinfo.primres, rel=1e-6)
+    assert mod.info.dualres == pytest.approx(oinfo.dualres, rel=1e-6)
+    assert mod.info.mismatch == pytest.approx(oinfo.mismatch, rel=1e-6)
+    np.testing.assert_allclose(mod.solution.u_curr, om.vec("u_curr"), atol=1e-7, rtol=0)
+    mod.close()
+
+
+def _lockstep(grid_or_case, rho_pq, rho_va, n_iter, fused, tol=ITERATE_TOL, scale=1e-4, outer_updates=()):
+    """Run oracle and CUDA side by side from the same start, compare every field after
+    every inner iteration."""
+    if isinstance(grid_or_case, str):
+        data = ea.parse_matpower(grid_or_case)
+    else:
+        data = grid_or_case
+    env = AdmmEnv(data, rho_pq, rho_va, use_gpu=True, verbose=0, tight_factor=0.99)
+    mod = ModelAcopf(env)
+    par = env.params
+    par.scale = scale
+    opar = Parameters(); opar.verbose = 0; opar.scale = scale
+    om = OracleModel(mod.grid_data, opar, rho_pq, rho_va)
+    ops.admm_increment_outer(env, mod); ops.admm_outer_prestep(env, mod); ops.admm_increment_reset_inner(env, mod)
+    om.admm_increment_outer(); om.admm_outer_prestep(); om.admm_increment_reset_inner()
+    worst = {}
+    for it in range(1, n_iter + 1):
+        ores = om.inner_iteration()
+        ops.admm_increment_inner(env, mod)
+        if fused:
+            ops.admm_inner_iteration(env, mod)
+        else:
+            ops.admm_inner_prestep(env, mod); ops.admm_update_x(env, mod); ops.admm_update_xbar(env, mod)
+            ops.admm_update_z(env, mod); ops.admm_update_l(env, mod); ops.admm_update_residual(env, mod)
+        for name in ("u_curr", "v_curr", "z_curr", "z_prev"):
+            d = np.abs(getattr(mod.solution, name) - om.vec(name)).max()
+            worst[name] = max(worst.get(name, 0.0), d)
+        dl = np.abs(mod.solution.l_curr - om.vec("l_curr")).max() / par.beta     # lambda = -(lz + beta z)
+        worst["l_curr/beta"] = max(worst.get("l_curr/beta", 0.0), dl)
+        got = np.array([mod.info.primres, mod.info.dualres, mod.info.norm_z_curr, mod.info.mismatch])
+        np.testing.assert_allclose(got, ores, rtol=1e-6, atol=1e-9)
+        if it in outer_updates:                                        # exercise lz / beta updates too
+            ops.admm_update_lz(env, mod); om.admm_update_lz()
+            par.beta *= 6.0; opar.beta *= 6.0
+            ops.admm_increment_outer(env, mod); ops.admm_increment_reset_inner(env, mod)
+            om.admm_increment_outer(); om.admm_increment_reset_inner()
+    mb = mod.membuf
+    omb = om.membuf()
+    np.testing.assert_array_equal(mb[26], omb[26])                    # mu (row 27): powers of ten, exact
+    worst["lambda_s/mu"] = float((np.abs(mb[24:26] - omb[24:26]) / np.maximum(1.0, omb[26])).max())
+    mod.close()
+    for k, v in worst.items():
+        assert v <= tol, (k, v, worst)
+    return worst
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_per_iterate_parity_case9(fused):
+    _lockstep(ea.CASE9, 4e2, 4e4, 60, fused, outer_updates=(20, 45))
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_per_iterate_parity_synthetic_300(fused):
+    d = synthetic_case(300, 40, 420, seed=300)
+    _lockstep(d, 4e2, 4e4, 40, fused, outer_updates=(25,))
+
+
+def test_per_iterate_parity_synthetic_binding_limits():
+    d = synthetic_case(200, 30, 280, seed=200, rate_margin=1.02)
+    _lockstep(d, 4e2, 4e4, 30, True)
+
+
+def test_per_iterate_parity_case1354_like():
+    d = synthetic_case(1354, 260, 1991, seed=1354)
+    _lockstep(d, 1e1, 1e3, 25, True)
+
+
+def test_fused_and_stepwise_paths_agree_bitwise():
+    d = synthetic_case(500, 60, 700, seed=500)
+    outs = []
+    for fused in (False, True):
+        env = AdmmEnv(d, 4e2, 4e4, use_gpu=True, verbose=0)
+        mod = ModelAcopf(env)
+        ops.admm_increment_outer(env, mod); ops.admm_outer_prestep(env, mod); ops.admm_increment_reset_inner(env, mod)
+        for _ in range(15):
+            ops.admm_increment_inner(env, mod)
+            if fused:
+                ops.admm_inner_iteration(env, mod)
+            else:
+                ops.admm_inner_prestep(env, mod); ops.admm_update_x(env, mod); ops.admm_update_xbar(env, mod)
+                ops.admm_update_z(env, mod); ops.admm_update_l(env, mod); ops.admm_update_residual(env, mod)
+        outs.append({k: getattr(mod.solution, k) for k in ("u_curr", "v_curr", "z_curr", "z_prev", "l_curr")})
+        outs[-1]["res"] = np.array([mod.info.primres, mod.info.dualres, mod.info.norm_z_curr, mod.info.mismatch])
+        mod.close()
+    for k in ("u_curr", "v_curr", "z_curr", "z_prev", "l_curr"):
+        np.testing.assert_array_equal(outs[0][k], outs[1][k])
+    np.testing.assert_allclose(outs[0]["res"], outs[1]["res"], rtol=1e-13)     # reduction order differs
+
+
+def test_run_inner_stops_on_the_same_iteration_as_the_host_loop():
+    d = synthetic_case(300, 40, 420, seed=301)
+    counts = []
+    for mode in ("stepwise", "fused", "native"):
+        env = AdmmEnv(d, 4e2, 4e4, use_gpu=True, verbose=0)
+        mod = ModelAcopf(env)
+        env.params.outer_iterlim = 3; env.params.inner_iterlim = 400
+        admm_two_level(env, mod, None, mode=mode)
+        counts.append((mod.info.outer, mod.info.cumul, mod.info.inner, mod.info.status, mod.solution.u_curr))
+        mod.close()
+    assert counts[0][:4] == counts[1][:4] == counts[2][:4]
+    np.testing.assert_array_equal(counts[0][4], counts[1][4])
+    np.testing.assert_array_equal(counts[0][4], counts[2][4])
+
+
+def test_vector_and_membuf_round_trip(case9_grid):
+    env, mod = _env_mod(ea.CASE9)
+    rng = np.random.default_rng(0)
+    for name in ("u_curr", "v_curr", "l_curr", "rho", "z_curr", "z_prev", "lz", "rp", "u_prev", "z_outer"):
+        x = rng.normal(size=mod.nvar)
+        setattr(mod.solution, name, x)
+        np.testing.assert_array_equal(getattr(mod.solution, name), x)
+    assert mod.membuf.shape == (31, 9)
+    np.testing.assert_array_equal(mod.membuf[28], case9_grid.rateA)      # row 29 = rateA (acopf_model.jl:89)
+    mod.set_membuf_row(25, np.arange(9.0)); mod.set_membuf_row(27, np.full(9, 100.0))
+    np.testing.assert_array_equal(mod.membuf[24], np.arange(9.0))
+    np.testing.assert_array_equal(mod.membuf[26], np.full(9, 100.0))
+    # rows 1-24 are the reference's staging of lambda, rho, xbar - z
+    l = mod.solution.l_curr; v = mod.solution.v_curr; z = mod.solution.z_curr
+    mb = mod.membuf
+    np.testing.assert_array_equal(mb[0:8].T.ravel(), l[6:])
+    np.testing.assert_allclose(mb[16:24].T.ravel(), (v - z)[6:], rtol=0, atol=0)
+    with pytest.raises(Exception):
+        mod.set_vector("u_curr", np.zeros(3))
+    mod.close()
+
+
+def test_empty_and_ragged_grids():
+    """Edge cases: a bus with no generator and no load, parallel lines, a bus with many
+    lines, generators sharing a bus, a line at the reference bus."""
+    txt = open(ea.CASE9).read()
+    txt = txt.replace("\t3\t85\t-10.95", "\t2\t85\t-10.95")          # gens 2 and 3 share bus 2
+    txt = txt.replace("];\n\n%% generator cost", "\t5\t6\t0.039\t0.17\t0.358\t150\t150\t150\t0\t0\t1\t-360\t360;\n];\n\n%% generator cost")
+    d = ea.parse_matpower_text(txt)
+    assert d.nline == 10
+    _lockstep(d, 4e2, 4e4, 30, True)
+    _lockstep(d, 4e2, 4e4, 30, False)
+
+
+def test_set_load_changes_only_the_bus_update(case9_grid):
+    env, mod = _env_mod(ea.CASE9)
+    par = Parameters(); par.verbose = 0
+    om = OracleModel(case9_grid, par, 4e2, 4e4)
+    Pd = case9_grid.Pd * 1.05; Qd = case9_grid.Qd * 0.95
+    mod.set_load(Pd, Qd); om.set_load(Pd, Qd)
+    ops.admm_increment_outer(env, mod); ops.admm_increment_inner(env, mod)
+    om.admm_increment_outer()
+    for _ in range(5):
+        om.inner_iteration()
+        ops.admm_inner_iteration(env, mod); ops.admm_increment_inner(env, mod)
+    np.testing.assert_allclose(mod.solution.v_curr, om.vec("v_curr"), atol=ITERATE_TOL, rtol=0)
+    mod.close()
