@@ -48,6 +48,7 @@ WORKLOADS = {
     "case13659pegase": ("case13659pegase", 5e1, 5e3, 1e-4),
     "case1354pegase": ("case1354pegase", 1e1, 1e3, 1e-4),
     "case2869pegase": ("case2869pegase", 1e1, 1e3, 1e-4),
+    "tiny": ("tiny", 4e2, 4e4, 1e-4),          # 200 buses / 280 branches: latency probe (one branch per warp)
 }
 
 
@@ -55,8 +56,11 @@ def make_grid(workload):
     import exaadmm_b200 as ea
     from exaadmm_b200.synthetic import named_case
     name = WORKLOADS[workload][0]
-    cache = ROOT / "gpurun_out" / f".cache_{name}.npz"
-    data = named_case(name)
+    if name == "tiny":
+        from exaadmm_b200.synthetic import synthetic_case
+        data = synthetic_case(200, 30, 280, seed=200)
+    else:
+        data = named_case(name)
     return ea.GridData.from_opfdata(data, tight_factor=0.99), data
 
 

@@ -7,15 +7,22 @@
 // (AL loop), acopf_tron_linelimit_kernel.jl:4-149 (TRON driver) and
 // acopf_eval_linelimit_kernel_gpu.jl:1-594 (f, grad, Hessian).
 //
-// One thread owns one branch. The objective uses the structure every flow
+// One lane owns one branch at a time. The objective uses the structure every flow
 // shares, F = a vi^2 + b vj^2 + vi vj P(t), t = ti - tj:
 // gradient and Hessian are assembled in the 3 variables (vi, vj, t) from
 // aggregated flow weights and then expanded to the 6x6 packed matrix, one
-// sincos per evaluation, f/grad/Hessian fused. The AL loop and the TRON
-// reverse-communication loop are flattened into ONE loop whose body is
-//   [compute trial step]  ->  [evaluate f,g,H]  ->  [judge / converge / AL update]
-// so lanes of a warp that are in different TRON iterations or different AL
-// iterations still run the same instructions.
+// sincos per evaluation, f/grad/Hessian fused.
+//
+// The AL loop and TRON's reverse-communication loop are flattened into a state
+// machine (`Lane`) advanced by three uniform phases per round,
+//     eval_pass(0)  lanes holding a trial point: evaluate, judge, converge, AL update
+//     eval_pass(1)  lanes starting a TRON solve (new branch, next AL iteration, or a
+//                   rejected step): evaluate at the current point
+//     compute()     every live lane: Cauchy point + projected CG -> next trial point
+// so that the lanes of a warp, each at a different stage of a different branch,
+// execute the same instructions. The kernel (kernels.cuh) refills finished lanes
+// with new branches between the phases; the host test harness drives the very same
+// three functions for one branch.
 #pragma once
 #include "tron.cuh"
 
@@ -31,44 +38,58 @@ struct Data {          // per-branch inputs, reference rows in comments (membuf 
     double Y[8];       // YffR,YffI,YftR,YftI,YttR,YttI,YtfR,YtfI
 };
 
+// Views of the per-branch data: a plain struct (host harness) or one column of a
+// shared-memory tile (kernel; element k of lane t lives at base[k * STRIDE], which is
+// bank-conflict free for a warp).
+struct StructView {
+    const Data *d;
+    EA_DEV double lam(int k) const { return d->lam[k]; }
+    EA_DEV double rho(int k) const { return d->rho[k]; }
+    EA_DEV double xt(int k) const { return d->xt[k]; }
+    EA_DEV double Y(int k) const { return d->Y[k]; }
+};
+template <int STRIDE> struct TileView {
+    const double *base;                                  // &tile[0][lane]
+    EA_DEV double lam(int k) const { return base[k * STRIDE]; }
+    EA_DEV double rho(int k) const { return base[(8 + k) * STRIDE]; }
+    EA_DEV double xt(int k) const { return base[(16 + k) * STRIDE]; }
+    EA_DEV double Y(int k) const { return base[(24 + k) * STRIDE]; }
+};
+constexpr int TILE_ROWS = 32 + 9;                        // lam, rho, xt, Y + xl0..3, xu0..3, rateA
+
 struct PowTable {      // host-computed (glibc) 1/mu^0.1 and mu^0.9 for the mu sequence 10, 100, ... <= mu_max
     int n;
     double mu[24], inv_p01[24], p09[24];
 };
 
-struct Work { int auglag = 0, evals = 0, cg = 0, shifts = 0, rejected = 0, hit_max = 0; };
-
+__host__ __device__ __noinline__ inline void mu_powers_general(double mu, double *inv_p01, double *p09) {
+    *inv_p01 = 1.0 / pow(mu, 0.1);          // only if mu was set from outside to something off the 10^k ladder
+    *p09 = pow(mu, 0.9);
+}
 EA_DEV void mu_powers(const PowTable &T, double mu, double &inv_p01, double &p09) {
 #pragma unroll 1
     for (int k = 0; k < T.n; ++k)
         if (T.mu[k] == mu) { inv_p01 = T.inv_p01[k]; p09 = T.p09[k]; return; }
-    inv_p01 = 1.0 / pow(mu, 0.1);
-    p09 = pow(mu, 0.9);
+    double a, b;
+    mu_powers_general(mu, &a, &b);
+    inv_p01 = a; p09 = b;
 }
 
-// flows at x: F[0..3] = pij, qij, pji, qji (acopf_eval_linelimit_kernel_gpu.jl:17-22)
-EA_DEV void flows(const double (&x)[N], const double (&Y)[8], double (&F)[4]) {
-    double s, c;
-    sincos(x[2] - x[3], &s, &c);
-    const double vv = x[0] * x[1], vi2 = x[0] * x[0], vj2 = x[1] * x[1];
-    F[0] = Y[0] * vi2 + vv * (Y[2] * c + Y[3] * s);
-    F[1] = -Y[1] * vi2 + vv * (-Y[3] * c + Y[2] * s);
-    F[2] = Y[4] * vj2 + vv * (Y[6] * c - Y[7] * s);
-    F[3] = -Y[5] * vj2 + vv * (-Y[7] * c - Y[6] * s);
-}
-
-// Fused f, grad f, Hessian (packed lower) of the scaled branch AL objective, and the four flows.
-EA_DEV void eval_fgh(const Data &D, const double (&ls)[2], double mu, double scale,
-                                         const double (&x)[N], double &f, double (&g)[N], Sym6 &A, double (&F)[4]) {
+// Fused f, grad f, Hessian (packed lower) of the scaled branch AL objective, and the four
+// flows F = (pij, qij, pji, qji) (acopf_eval_linelimit_kernel_gpu.jl:17-22).
+template <class View>
+EA_DEV void eval_fgh(const View &D, const double (&ls)[2], double mu, double scale,
+                     const double (&x)[N], double &f, double (&g)[N], Sym6 &A, double (&F)[4]) {
     const double vi = x[0], vj = x[1];
     double s, c;
     sincos(x[2] - x[3], &s, &c);
     const double vv = vi * vj, vi2 = vi * vi, vj2 = vj * vj;
+    const double Y0 = D.Y(0), Y1 = D.Y(1), Y2 = D.Y(2), Y3 = D.Y(3), Y4 = D.Y(4), Y5 = D.Y(5), Y6 = D.Y(6), Y7 = D.Y(7);
     // per-flow a, b, gamma, delta
-    const double a[4] = { D.Y[0], -D.Y[1], 0.0, 0.0 };
-    const double b[4] = { 0.0, 0.0, D.Y[4], -D.Y[5] };
-    const double ga[4] = { D.Y[2], -D.Y[3], D.Y[6], -D.Y[7] };
-    const double de[4] = { D.Y[3], D.Y[2], -D.Y[7], -D.Y[6] };
+    const double a[4] = { Y0, -Y1, 0.0, 0.0 };
+    const double b[4] = { 0.0, 0.0, Y4, -Y5 };
+    const double ga[4] = { Y2, -Y3, Y6, -Y7 };
+    const double de[4] = { Y3, Y2, -Y7, -Y6 };
     double P[4], Q[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -80,19 +101,7 @@ EA_DEV void eval_fgh(const Data &D, const double (&ls)[2], double mu, double sca
     const double c2 = F[2] * F[2] + F[3] * F[3] + x[5];
     const double m[2] = { ls[0] + mu * c1, ls[1] + mu * c2 };
 
-    // objective
-    double fv = 0.0;
-    {
-        const double h[8] = { F[0], F[1], F[2], F[3], vi2, vj2, x[2], x[3] };
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const double d = h[k] - D.xt[k];
-            fv += D.lam[k] * h[k] + 0.5 * (D.rho[k] * (d * d));
-        }
-        fv += ls[0] * c1 + ls[1] * c2 + 0.5 * (mu * (c1 * c1)) + 0.5 * (mu * (c2 * c2));
-    }
-    f = scale * fv;
-
+    double fv = ls[0] * c1 + ls[1] * c2 + 0.5 * (mu * (c1 * c1)) + 0.5 * (mu * (c2 * c2));
     // reduced (vi, vj, t) gradient / Hessian
     double As = 0.0, Bs = 0.0, Ps = 0.0, Qs = 0.0;        // sum_k w_k * (a,b,P,Q)_k
     double H00 = 0.0, H01 = 0.0, H02 = 0.0, H11 = 0.0, H12 = 0.0, H22 = 0.0;
@@ -100,12 +109,15 @@ EA_DEV void eval_fgh(const Data &D, const double (&ls)[2], double mu, double sca
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int j = k >> 1;
+        const double lam = D.lam(k), rho = D.rho(k);
+        const double dev = F[k] - D.xt(k);
+        fv += lam * F[k] + 0.5 * (rho * (dev * dev));
         const double G0 = 2.0 * a[k] * vi + vj * P[k];
         const double G1 = 2.0 * b[k] * vj + vi * P[k];
         const double G2 = vv * Q[k];
-        const double r = D.lam[k] + D.rho[k] * (F[k] - D.xt[k]);
+        const double r = lam + rho * dev;
         const double w = r + 2.0 * m[j] * F[k];
-        const double kap = D.rho[k] + 2.0 * m[j];
+        const double kap = rho + 2.0 * m[j];
         As += w * a[k]; Bs += w * b[k]; Ps += w * P[k]; Qs += w * Q[k];
         const double tF = 2.0 * F[k];
         d[j][0] += tF * G0; d[j][1] += tF * G1; d[j][2] += tF * G2;
@@ -121,18 +133,25 @@ EA_DEV void eval_fgh(const Data &D, const double (&ls)[2], double mu, double sca
         H00 += m0 * d[j][0]; H01 += m0 * d[j][1]; H02 += m0 * d[j][2];
         H11 += m1 * d[j][1]; H12 += m1 * d[j][2]; H22 += m2 * d[j][2];
     }
-    const double ri = D.lam[4] + D.rho[4] * (vi2 - D.xt[4]);
-    const double rj = D.lam[5] + D.rho[5] * (vj2 - D.xt[5]);
+    // consensus terms on w_i = vi^2, w_j = vj^2, t_i, t_j
+    const double rho4 = D.rho(4), rho5 = D.rho(5), rho6 = D.rho(6), rho7 = D.rho(7);
+    const double dwi = vi2 - D.xt(4), dwj = vj2 - D.xt(5), dti = x[2] - D.xt(6), dtj = x[3] - D.xt(7);
+    const double lam4 = D.lam(4), lam5 = D.lam(5), lam6 = D.lam(6), lam7 = D.lam(7);
+    fv += lam4 * vi2 + 0.5 * (rho4 * (dwi * dwi)) + lam5 * vj2 + 0.5 * (rho5 * (dwj * dwj))
+        + lam6 * x[2] + 0.5 * (rho6 * (dti * dti)) + lam7 * x[3] + 0.5 * (rho7 * (dtj * dtj));
+    f = scale * fv;
+    const double ri = lam4 + rho4 * dwi;
+    const double rj = lam5 + rho5 * dwj;
     const double gy0 = 2.0 * As * vi + vj * Ps + 2.0 * vi * ri;
     const double gy1 = 2.0 * Bs * vj + vi * Ps + 2.0 * vj * rj;
     const double gy2 = vv * Qs;
-    H00 += 2.0 * ri + 4.0 * D.rho[4] * vi2;
-    H11 += 2.0 * rj + 4.0 * D.rho[5] * vj2;
+    H00 += 2.0 * ri + 4.0 * rho4 * vi2;
+    H11 += 2.0 * rj + 4.0 * rho5 * vj2;
 
     g[0] = scale * gy0;
     g[1] = scale * gy1;
-    g[2] = scale * (gy2 + D.lam[6] + D.rho[6] * (x[2] - D.xt[6]));
-    g[3] = scale * (-gy2 + D.lam[7] + D.rho[7] * (x[3] - D.xt[7]));
+    g[2] = scale * (gy2 + lam6 + rho6 * dti);
+    g[3] = scale * (-gy2 + lam7 + rho7 * dtj);
     g[4] = scale * m[0];
     g[5] = scale * m[1];
 
@@ -143,11 +162,11 @@ EA_DEV void eval_fgh(const Data &D, const double (&ls)[2], double mu, double sca
     A.a[tri(1, 1)] = scale * H11;
     A.a[tri(2, 0)] = scale * H02;
     A.a[tri(2, 1)] = scale * H12;
-    A.a[tri(2, 2)] = scale * (H22 + D.rho[6]);
+    A.a[tri(2, 2)] = scale * (H22 + rho6);
     A.a[tri(3, 0)] = -(scale * H02);
     A.a[tri(3, 1)] = -(scale * H12);
     A.a[tri(3, 2)] = -(scale * H22);
-    A.a[tri(3, 3)] = scale * (H22 + D.rho[7]);
+    A.a[tri(3, 3)] = scale * (H22 + rho7);
     A.a[tri(4, 0)] = smu * d[0][0];
     A.a[tri(4, 1)] = smu * d[0][1];
     A.a[tri(4, 2)] = smu * d[0][2];
@@ -161,133 +180,157 @@ EA_DEV void eval_fgh(const Data &D, const double (&ls)[2], double mu, double sca
     A.a[tri(5, 5)] = smu;
 }
 
-// The branch objective with its augmented-Lagrangian state (membuf rows 25-27).
-struct Objective {
-    const Data &D;
-    double ls[2];      // line-limit multipliers
-    double mu;         // AL penalty
+// The branch objective bound to a data view (what the kernel and the harness plug into Lane).
+template <class View> struct Objective {
+    View D;
     double scale;
-    EA_DEV void eval(const double (&x)[N], double &f, double (&g)[N], Sym6 &A, double (&F)[4]) const {
+    EA_DEV void operator()(const double (&x)[N], const double (&ls)[2], double mu, double &f, double (&g)[N],
+                           Sym6 &A, double (&F)[4]) const {
         eval_fgh(D, ls, mu, scale, x, f, g, A, F);
     }
 };
 
-// Solve one branch sub-problem: AL loop on the two line limits around TRON, flattened
-// into one loop. x: start point in, solution out. obj.ls / obj.mu are updated in place.
-// Returns the flows at the solution in Fout. `Obj` only needs eval(), ls[2] and mu, so
-// the test harness can run this same loop on another evaluator.
-template <class Obj>
-EA_DEV void solve(Obj &obj, const double (&xl)[N], const double (&xu)[N], double (&x)[N],
-                  int max_auglag, double mu_max, const PowTable &T, double (&Fout)[4], Work &wk) {
-    double (&ls)[2] = obj.ls;
-    double &mu = obj.mu;
+enum Phase : int { NEED = 0, START = 1, RESTORE = 2, TRIAL = 3, DONE = 4 };
+
+// State of one branch solve (registers).
+struct Lane {
+    double x[N], xc[N], g[N];
+    Sym6 A;
+    double ls[2], mu;                       // AL state (membuf rows 25-27)
+    double f, fc, delta, alphac, prered, g0, snorm, eta, inv_p01, p09;
+    double Fc[4];                           // flows at the current accepted point
+    int nfev, minor, iter, it_al;
+    int phase;
+    bool step_pending;
+    // work of the current branch
+    int evals, cg, shifts, rejected, hit_max;
+};
+
+// Start a branch: x, ls, mu must be set by the caller (mu = 10 on the first inner
+// iteration of an outer iteration, acopf_auglag_linelimit_kernel_gpu.jl:75-80).
+EA_DEV void begin(Lane &L, const PowTable &T) {
+    mu_powers(T, L.mu, L.inv_p01, L.p09);
+    L.eta = L.inv_p01;                       // eta = 1/mu^0.1 (:84)
+    L.f = L.fc = L.delta = L.prered = L.g0 = L.snorm = 0.0;
+    L.alphac = 1.0;
+    L.nfev = 0; L.minor = 0; L.iter = 1; L.it_al = 0;
+    L.phase = START;
+    L.step_pending = false;
+    L.evals = L.cg = L.shifts = L.rejected = L.hit_max = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { L.g[i] = 0.0; L.xc[i] = L.x[i]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) L.Fc[k] = 0.0;
+}
+
+// One evaluation phase. pass 0 serves lanes holding a trial point, pass 1 lanes at
+// the start of a TRON solve (or re-evaluating after a rejected step). Returns true
+// when the branch is finished (x, Fc, ls, mu hold the result).
+template <class Eval>
+EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N], const double (&xu)[N],
+                      int max_auglag, double mu_max, const PowTable &T) {
     const int max_feval = 500, max_minor = 200;     // call site acopf_auglag_linelimit_kernel_gpu.jl:94
     const double gtol = 1e-6;
-    double inv_p01, p09;
-    mu_powers(T, mu, inv_p01, p09);
-    double eta = inv_p01;                            // eta = 1/mu^0.1 (:84)
+    const bool mine = (pass == 0) ? (L.phase == TRIAL) : (L.phase == START || L.phase == RESTORE);
+    if (!mine) return false;
 
-    // TRON state. g and A always belong to the last evaluated point; a rejected
-    // step (rare) re-evaluates them at x_c (phase RESTORE) instead of keeping a copy.
-    double f = 0.0, fc = 0.0, delta = 0.0, alphac = 1.0, prered = 0.0, g0 = 0.0, snorm = 0.0;
-    double g[N], xc[N];
-    Sym6 A;
-    double Fc[4] = { 0.0, 0.0, 0.0, 0.0 };           // flows at the current accepted point
-    int nfev = 0, minor = 0, iter = 1, it_al = 0;
-    enum { START = 0, TRIAL = 1, RESTORE = 2 };
-    int phase = START;
-    bool step_pending = false;
-    tron::Stats st;
-#pragma unroll
-    for (int i = 0; i < N; ++i) { g[i] = 0.0; xc[i] = x[i]; }
+    double fn, Fn[4];
+    eval(L.x, L.ls, L.mu, fn, L.g, L.A, Fn);        // g, A always belong to the last evaluated point
+    if (L.phase != RESTORE) L.evals++;               // counted like the reference's f-evaluations
 
-#pragma unroll 1
-    for (;;) {
-        if (step_pending) {
-            // dtron COMPUTE: Cauchy point + projected CG -> trial point in x
-            fc = f;
+    if (pass == 1) {
+        L.f = fn;
 #pragma unroll
-            for (int i = 0; i < N; ++i) xc[i] = x[i];
-            tron::compute_step<N>(x, xl, xu, A, g, delta, alphac, prered, g0, snorm, st);
-            phase = TRIAL;
-            step_pending = false;
+        for (int k = 0; k < 4; ++k) L.Fc[k] = Fn[k];
+        if (L.phase == START) {                      // task 0: a fresh TRON solve
+            L.nfev = 1; L.minor = 1; L.iter = 1; L.alphac = 1.0;
+            L.delta = tron::nrm2<N>(L.g);            // tron_kernel.jl:102-105
         }
+        L.step_pending = true;
+        return false;
+    }
 
-        double fn, Fn[4];
-        obj.eval(x, fn, g, A, Fn);
-        if (phase != RESTORE) wk.evals++;              // counted like the reference's f-evaluations
-        bool tron_done = false;
-        if (phase == TRIAL) {
-            nfev++;
-            if (nfev >= max_feval) {
-                tron_done = true;                    // driver stops, trial point kept (tron_kernel.jl:72-75)
+    bool tron_done = false;
+    L.nfev++;
+    if (L.nfev >= max_feval) {
+        tron_done = true;                            // driver stops, trial point kept (tron_kernel.jl:72-75)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) Fc[k] = Fn[k];
-            } else {
-                bool accepted;
-                const int task = tron::judge_step(fn, fc, g0, snorm, prered, iter == 1, delta, accepted);
-                if (accepted) {
-                    iter++;
-                    f = fn;
+        for (int k = 0; k < 4; ++k) L.Fc[k] = Fn[k];
+    } else {
+        bool accepted;
+        const int task = tron::judge_step(fn, L.fc, L.g0, L.snorm, L.prered, L.iter == 1, L.delta, accepted);
+        if (accepted) {
+            L.iter++;
+            L.f = fn;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) Fc[k] = Fn[k];
-                    if (task == 2) tron_done = true;
-                    else {
-                        minor++;                      // the reference evaluates g,H here (task GH)
-                        if (tron::gpnorm<N>(x, xl, xu, g) <= gtol) tron_done = true;          // NEWX test (:121-130)
-                        else if (minor >= max_minor) tron_done = true;
-                        else step_pending = true;
-                    }
-                } else {
-                    wk.rejected++;
-#pragma unroll
-                    for (int i = 0; i < N; ++i) x[i] = xc[i];
-                    f = fc;
-                    if (task == 2) tron_done = true;   // Fc still holds the flows at xc
-                    else phase = RESTORE;              // g, A must be re-evaluated at xc before the next step
-                }
+            for (int k = 0; k < 4; ++k) L.Fc[k] = Fn[k];
+            if (task == 2) tron_done = true;
+            else {
+                L.minor++;                            // the reference evaluates g,H here (task GH)
+                if (tron::gpnorm<N>(L.x, xl, xu, L.g) <= gtol) tron_done = true;          // NEWX test (:121-130)
+                else if (L.minor >= max_minor) tron_done = true;
+                else L.step_pending = true;
             }
         } else {
-            f = fn;
+            L.rejected++;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) Fc[k] = Fn[k];
-            if (phase == START) {                      // task 0: a fresh TRON solve
-                nfev = 1; minor = 1; iter = 1; alphac = 1.0;
-                delta = tron::nrm2<N>(g);              // tron_kernel.jl:102-105
-            }
-            step_pending = true;
-        }
-
-        if (tron_done) {
-            // augmented-Lagrangian update on the line limits (auglag_gpu.jl:96-131)
-            it_al++;
-            const double cviol1 = Fc[0] * Fc[0] + Fc[1] * Fc[1] + x[4];
-            const double cviol2 = Fc[2] * Fc[2] + Fc[3] * Fc[3] + x[5];
-            const double cnorm = fmax(fabs(cviol1), fabs(cviol2));
-            bool terminate = false;
-            if (cnorm <= eta) {
-                if (cnorm <= 1e-6) terminate = true;
-                else {
-                    ls[0] += mu * cviol1;
-                    ls[1] += mu * cviol2;
-                    eta = eta / p09;
-                }
-            } else {
-                mu = fmin(mu_max, mu * 10.0);
-                mu_powers(T, mu, inv_p01, p09);
-                eta = inv_p01;
-            }
-            if (it_al >= max_auglag) { if (!terminate) wk.hit_max = 1; terminate = true; }
-            if (terminate) break;
-            phase = START;
-            step_pending = false;
+            for (int i = 0; i < N; ++i) L.x[i] = L.xc[i];
+            L.f = L.fc;
+            if (task == 2) tron_done = true;          // Fc still holds the flows at xc
+            else L.phase = RESTORE;                   // g, A must be re-evaluated at xc before the next step
         }
     }
+    if (!tron_done) return false;
+
+    // augmented-Lagrangian update on the line limits (auglag_gpu.jl:96-131)
+    L.it_al++;
+    const double cviol1 = L.Fc[0] * L.Fc[0] + L.Fc[1] * L.Fc[1] + L.x[4];
+    const double cviol2 = L.Fc[2] * L.Fc[2] + L.Fc[3] * L.Fc[3] + L.x[5];
+    const double cnorm = tron::dmax(fabs(cviol1), fabs(cviol2));
+    bool terminate = false;
+    if (cnorm <= L.eta) {
+        if (cnorm <= 1e-6) terminate = true;
+        else {
+            L.ls[0] += L.mu * cviol1;
+            L.ls[1] += L.mu * cviol2;
+            L.eta = L.eta / L.p09;
+        }
+    } else {
+        L.mu = tron::dmin(mu_max, L.mu * 10.0);
+        mu_powers(T, L.mu, L.inv_p01, L.p09);
+        L.eta = L.inv_p01;
+    }
+    if (L.it_al >= max_auglag) { if (!terminate) L.hit_max = 1; terminate = true; }
+    if (terminate) { L.phase = DONE; return true; }
+    L.phase = START;
+    return false;
+}
+
+// dtron COMPUTE for lanes with a pending step: Cauchy point + projected CG -> trial point in x.
+EA_DEV void compute(Lane &L, const double (&xl)[N], const double (&xu)[N]) {
+    if (!L.step_pending) return;
+    L.fc = L.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) Fout[k] = Fc[k];
-    wk.auglag = it_al;
-    wk.cg = st.cg;
-    wk.shifts = st.shifts;
+    for (int i = 0; i < N; ++i) L.xc[i] = L.x[i];
+    tron::Stats st;
+    tron::compute_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered, L.g0, L.snorm, st);
+    L.cg += st.cg;
+    L.shifts += st.shifts;
+    L.phase = TRIAL;
+    L.step_pending = false;
+}
+
+// Solve one branch to completion on one lane (host harness and diagnostics).
+template <class Eval>
+EA_DEV void solve(Lane &L, const Eval &eval, const double (&xl)[N], const double (&xu)[N],
+                  int max_auglag, double mu_max, const PowTable &T) {
+    begin(L, T);
+#pragma unroll 1
+    for (;;) {
+        if (eval_pass(L, eval, 0, xl, xu, max_auglag, mu_max, T)) break;
+        eval_pass(L, eval, 1, xl, xu, max_auglag, mu_max, T);
+        compute(L, xl, xu);
+    }
 }
 
 }  // namespace branch

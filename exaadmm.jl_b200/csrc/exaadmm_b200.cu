@@ -46,6 +46,7 @@ struct ea_handle {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     Timers tm;
     int default_chunk = 16;
+    int x_resident_blocks = 148;                // CTAs of k_xupdate resident on the device at once
     // launch accounting / optional per-kernel timing of the fused loop
     double span_s = 0.0;                        // device time spent inside ea_run_inner* calls (events on h->stream)
     long long n_x = 0, n_bus = 0, n_other = 0;  // kernels launched
@@ -119,10 +120,12 @@ int sync_ctrl_to_device(ea_handle *h, double beta, double eps_pri, long long inn
 
 int launch_x(ea_handle *h, long long major, int zsel, int max_auglag, double mu_max, double scale, int lines, int gens) {
     build_pow_table(h, mu_max);
-    const int line_blocks = (int)((h->nline + XBLOCK - 1) / XBLOCK);
-    const int gen_blocks = (int)((h->ngen + XBLOCK - 1) / XBLOCK);
-    const int grid = std::max(1, line_blocks + gen_blocks);
-    k_xupdate<<<grid, XBLOCK, 0, h->stream>>>(h->d, h->pow_table, major, zsel, max_auglag, mu_max, scale, lines, gens);
+    if (major > 0 && lines)     // step-wise call: the fused loop resets the work queue itself (k_bus / k_ctrl_begin)
+        CK(cudaMemsetAsync(&h->d.ctrl->next_line, 0, sizeof(int), h->stream));
+    // persistent grid: as many CTAs as are resident at once, capped by the work available
+    const int64_t work_blocks = std::max<int64_t>((h->nline + XBLOCK - 1) / XBLOCK, (h->ngen + XBLOCK - 1) / XBLOCK);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->x_resident_blocks, work_blocks));
+    k_xupdate<<<grid, XBLOCK, XTILE_BYTES, h->stream>>>(h->d, h->pow_table, major, zsel, max_auglag, mu_max, scale, lines, gens);
     CK(cudaGetLastError());
     h->n_x++;
     return EA_OK;
@@ -165,6 +168,14 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     if (cudaEventCreate(&h->span0) != cudaSuccess || cudaEventCreate(&h->span1) != cudaSuccess)
         return bail(fail(h, EA_ERR_CUDA, "cudaEventCreate failed"));
 
+    {
+        int per_sm = 0, sms = 0;
+        if (cudaFuncSetAttribute(k_xupdate, cudaFuncAttributeMaxDynamicSharedMemorySize, XTILE_BYTES) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xupdate, XBLOCK, XTILE_BYTES) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1)
+            return bail(fail(h, EA_ERR_CUDA, "k_xupdate occupancy query failed: %s", cudaGetErrorString(cudaGetLastError())));
+        h->x_resident_blocks = per_sm * sms;
+    }
     const int ngen = (int)G->ngen, nline = (int)G->nline, nbus = (int)G->nbus;
     h->ngen = ngen; h->nline = nline; h->nbus = nbus; h->nvar = 2 * (int64_t)ngen + 8 * (int64_t)nline;
     const int gpad = ((2 * ngen + 3) / 4) * 4;
@@ -550,6 +561,14 @@ int ea_get_kernel_times(ea_handle_t *h, double out[8]) {
     if (!h || !out) return EA_ERR_ARG;
     out[0] = h->span_s; out[1] = (double)h->n_x; out[2] = h->t_x; out[3] = (double)h->n_bus; out[4] = h->t_bus;
     out[5] = (double)h->n_other; out[6] = 0.0; out[7] = 0.0;
+    if (h->d.count_work > 1) {      // diagnostics: x-update phase split of the LAST launch since reset (seconds)
+        Counters c;
+        cudaStreamSynchronize(h->stream);
+        if (cudaMemcpy(&c, h->d.counters, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess && c.t[2] > c.t[0]) {
+            out[6] = 1e-9 * (double)(c.t[1] - c.t[0]);     // start -> work queue empty
+            out[7] = 1e-9 * (double)(c.t[2] - c.t[0]);     // start -> last warp done
+        }
+    }
     return EA_OK;
 }
 
@@ -713,13 +732,14 @@ int ea_reset_counters(ea_handle_t *h) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemset(h->d.counters, 0, sizeof(Counters)));
+    { unsigned long long big = ~0ull; CK(cudaMemcpy(&h->d.counters->t[0], &big, 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(&h->d.counters->t[1], &big, 8, cudaMemcpyHostToDevice)); }
     h->span_s = 0.0; h->n_x = h->n_bus = h->n_other = 0; h->t_x = h->t_bus = 0.0;
     return EA_OK;
 }
 
 int ea_set_option(ea_handle_t *h, const char *name, double value) {
     if (!h || !name) return EA_ERR_ARG;
-    if (!strcmp(name, "count_work")) { h->d.count_work = value != 0.0; return EA_OK; }
+    if (!strcmp(name, "count_work")) { h->d.count_work = (int)value; return EA_OK; }   // 2: also phase timestamps
     if (!strcmp(name, "chunk")) { h->default_chunk = std::max(1, (int)value); return EA_OK; }
     if (!strcmp(name, "kernel_timing")) { h->kernel_timing = value != 0.0; return EA_OK; }
     return fail(h, EA_ERR_ARG, "ea_set_option: unknown option '%s'", name);

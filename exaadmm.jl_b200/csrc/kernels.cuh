@@ -28,10 +28,10 @@ struct Ctrl {                 // device-resident loop control (one per handle)
     int done;                 // 1: primres <= eps_pri or inner == inner_limit; later launches are no-ops
     int zsel;                 // which of the two z buffers is z_curr
     unsigned ticket;          // last-block election for the residual reduction
-    int pad;
+    int next_line;            // work queue head of the branch kernel (reset for the next x-update)
 };
 
-struct Counters { unsigned long long v[8]; };
+struct Counters { unsigned long long v[8]; unsigned long long t[4]; };   // t: first start, queue empty, last end (globaltimer ns), launches
 
 struct Dev {                  // everything the kernels need, passed by value
     int ngen, nline, nbus, nint, gpad;
@@ -168,8 +168,22 @@ __global__ void k_init_solution(Dev d, double rho_pq, double rho_va) {
 // auglag_linelimit_two_level_alternative (acopf_auglag_linelimit_kernel_gpu.jl:1-151).
 //   major_arg > 0 : info.inner supplied by the host (step-wise API)
 //   major_arg == 0: read from the device control block (fused loop)
+//
+// Persistent grid (one CTA set resident per SM). Branches are handed out through a
+// work queue (ctrl->next_line): a lane that finishes its branch immediately takes
+// the next one, so the warp keeps all 32 lanes busy although branches need anything
+// from 2 to >100 objective evaluations. Per-branch inputs (lambda, rho, xbar - z,
+// admittances, bounds: 41 doubles) are staged in a shared-memory tile, one column
+// per lane; the TRON state lives in registers.
 // ---------------------------------------------------------------------------
-constexpr int XBLOCK = 128;
+#ifndef EA_XBLOCK
+#define EA_XBLOCK 128
+#endif
+#ifndef EA_XMINB
+#define EA_XMINB 1
+#endif
+constexpr int XBLOCK = EA_XBLOCK;
+constexpr int XTILE_BYTES = branch::TILE_ROWS * XBLOCK * 8;
 
 __device__ __forceinline__ void generator_update(const Dev &d, const double *z, int k) {
     const double2 x = *reinterpret_cast<const double2 *>(d.v + 2 * k);
@@ -184,9 +198,65 @@ __device__ __forceinline__ void generator_update(const Dev &d, const double *z, 
     *reinterpret_cast<double2 *>(d.u + 2 * k) = u;
 }
 
-__global__ void __launch_bounds__(XBLOCK)
+// Stage branch I into the lane's tile column and set the start point (auglag_gpu.jl:23-80).
+__device__ __forceinline__ void load_branch(const Dev &d, const double *z, int I, long long major, double *col,
+                                            branch::Lane &L) {
+    const int nl = d.nline;
+    const int sf = d.slot_from[I], st = d.slot_to[I];
+    const double *uh = d.u + d.gpad, *vh = d.v + d.gpad, *zh = z + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
+    const d4 lf = ld4(lh, sf), lt = ld4(lh, st);
+    const d4 rf = ld4(rh, sf), rt = ld4(rh, st);
+    const d4 vf = ld4(vh, sf), vt = ld4(vh, st), zf = ld4(zh, sf), zt = ld4(zh, st);
+    const d4 uf = ld4(uh, sf), ut = ld4(uh, st);
+    const double lam[8] = { lf.p, lf.q, lt.p, lt.q, lf.w, lt.w, lf.t, lt.t };
+    const double rho[8] = { rf.p, rf.q, rt.p, rt.q, rf.w, rt.w, rf.t, rt.t };
+    const double xt[8] = { vf.p - zf.p, vf.q - zf.q, vt.p - zt.p, vt.q - zt.q, vf.w - zf.w, vt.w - zt.w, vf.t - zf.t, vt.t - zt.t };
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        col[k * XBLOCK] = lam[k];
+        col[(8 + k) * XBLOCK] = rho[k];
+        col[(16 + k) * XBLOCK] = xt[k];
+        col[(24 + k) * XBLOCK] = d.Y[k * nl + I];
+    }
+    double b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { b[k] = d.xlu[k * nl + I]; col[(32 + k) * XBLOCK] = b[k]; }
+    const double ra = d.rateA[I];
+    col[40 * XBLOCK] = ra;
+    // start point from the previous u (auglag_gpu.jl:43-48); b = xl0,xu0,xl1,xu1,...
+    L.x[0] = fmin(b[1], fmax(b[0], sqrt(uf.w)));
+    L.x[1] = fmin(b[3], fmax(b[2], sqrt(ut.w)));
+    L.x[2] = fmin(b[5], fmax(b[4], uf.t));
+    L.x[3] = fmin(b[7], fmax(b[6], ut.t));
+    L.x[4] = fmin(0.0, fmax(-ra, -(uf.p * uf.p + uf.q * uf.q)));
+    L.x[5] = fmin(0.0, fmax(-ra, -(ut.p * ut.p + ut.q * ut.q)));
+    L.ls[0] = d.als[I];
+    L.ls[1] = d.als[nl + I];
+    L.mu = (major == 1) ? 10.0 : d.als[2 * nl + I];              // auglag_gpu.jl:75-80
+}
+
+__device__ __forceinline__ void load_bounds(const double *col, double (&xl)[6], double (&xu)[6]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { xl[k] = col[(32 + 2 * k) * XBLOCK]; xu[k] = col[(33 + 2 * k) * XBLOCK]; }
+    const double ra = col[40 * XBLOCK];
+    xl[4] = -ra; xu[4] = 0.0; xl[5] = -ra; xu[5] = 0.0;
+}
+
+// Write back u and the AL state of a finished branch (auglag_gpu.jl:135-145).
+__device__ __forceinline__ void store_branch(const Dev &d, int I, const branch::Lane &L) {
+    const int nl = d.nline;
+    d4 of, ot;
+    of.p = L.Fc[0]; of.q = L.Fc[1]; of.w = L.x[0] * L.x[0]; of.t = L.x[2];
+    ot.p = L.Fc[2]; ot.q = L.Fc[3]; ot.w = L.x[1] * L.x[1]; ot.t = L.x[3];
+    st4(d.u + d.gpad, d.slot_from[I], of);
+    st4(d.u + d.gpad, d.slot_to[I], ot);
+    d.als[I] = L.ls[0]; d.als[nl + I] = L.ls[1]; d.als[2 * nl + I] = L.mu;
+}
+
+__global__ void __launch_bounds__(XBLOCK, EA_XMINB)
 k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_auglag, double mu_max, double scale,
           int do_lines, int do_gens) {
+    extern __shared__ double tile[];                       // TILE_ROWS x XBLOCK
     long long major = major_arg;
     int zsel = zsel_arg;
     if (major_arg == 0) {
@@ -195,76 +265,85 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
         zsel = d.ctrl->zsel;
     }
     const double *z = d.zbuf[zsel];
-    const int t = blockIdx.x * XBLOCK + threadIdx.x;
-    const int line_threads = ((d.nline + XBLOCK - 1) / XBLOCK) * XBLOCK;   // generators start on a block boundary
-
-    if (t >= line_threads) {
-        const int k = t - line_threads;
-        if (do_gens && k < d.ngen) generator_update(d, z, k);
-        return;
-    }
+    if (do_gens)
+        for (int k = blockIdx.x * XBLOCK + threadIdx.x; k < d.ngen; k += gridDim.x * XBLOCK) generator_update(d, z, k);
     if (!do_lines) return;
 
-    branch::Work wk;
-    const bool active = t < d.nline;
-    if (active) {
-        const int I = t, nl = d.nline;
-        const int sf = d.slot_from[I], st = d.slot_to[I];
-        const double *uh = d.u + d.gpad, *vh = d.v + d.gpad, *zh = z + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
-        branch::Data D;
-        double x[6], xl[6], xu[6];
-        {
-            const d4 lf = ld4(lh, sf), lt = ld4(lh, st);
-            D.lam[0] = lf.p; D.lam[1] = lf.q; D.lam[2] = lt.p; D.lam[3] = lt.q;
-            D.lam[4] = lf.w; D.lam[5] = lt.w; D.lam[6] = lf.t; D.lam[7] = lt.t;
-            const d4 rf = ld4(rh, sf), rt = ld4(rh, st);
-            D.rho[0] = rf.p; D.rho[1] = rf.q; D.rho[2] = rt.p; D.rho[3] = rt.q;
-            D.rho[4] = rf.w; D.rho[5] = rt.w; D.rho[6] = rf.t; D.rho[7] = rt.t;
-            const d4 vf = ld4(vh, sf), vt = ld4(vh, st), zf = ld4(zh, sf), zt = ld4(zh, st);
-            D.xt[0] = vf.p - zf.p; D.xt[1] = vf.q - zf.q; D.xt[2] = vt.p - zt.p; D.xt[3] = vt.q - zt.q;
-            D.xt[4] = vf.w - zf.w; D.xt[5] = vt.w - zt.w; D.xt[6] = vf.t - zf.t; D.xt[7] = vt.t - zt.t;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) D.Y[k] = d.Y[k * nl + I];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { xl[k] = d.xlu[(2 * k) * nl + I]; xu[k] = d.xlu[(2 * k + 1) * nl + I]; }
-            const double ra = d.rateA[I];
-            xl[4] = -ra; xu[4] = 0.0; xl[5] = -ra; xu[5] = 0.0;
-            // start point from the previous u (auglag_gpu.jl:43-48)
-            const d4 uf = ld4(uh, sf), ut = ld4(uh, st);
-            x[0] = fmin(xu[0], fmax(xl[0], sqrt(uf.w)));
-            x[1] = fmin(xu[1], fmax(xl[1], sqrt(ut.w)));
-            x[2] = fmin(xu[2], fmax(xl[2], uf.t));
-            x[3] = fmin(xu[3], fmax(xl[3], ut.t));
-            x[4] = fmin(xu[4], fmax(xl[4], -(uf.p * uf.p + uf.q * uf.q)));
-            x[5] = fmin(xu[5], fmax(xl[5], -(ut.p * ut.p + ut.q * ut.q)));
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned long long t_now = 0;
+    if (d.count_work > 1 && threadIdx.x == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+        atomicMin(&d.counters->t[0], t_now);
+    }
+    bool saw_empty = false;
+    double *col = tile + threadIdx.x;
+    const branch::Objective<branch::TileView<XBLOCK>> eval{ { col }, scale };
+    branch::Lane L;
+    L.phase = branch::NEED;
+    L.step_pending = false;
+    int I = -1;
+    unsigned long long work[7] = { 0, 0, 0, 0, 0, 0, 0 };  // calls, auglag, evals, cg, shifts, rejected, hit_max
+    int mx = 0;
+
+#pragma unroll 1
+    for (;;) {
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            // refill: lanes without a branch take the next ones from the queue
+            const bool need = (L.phase == branch::NEED);
+            const unsigned m = __ballot_sync(full, need);
+            if (m) {
+                int base = 0;
+                if (lane == __ffs(m) - 1) base = atomicAdd(&d.ctrl->next_line, __popc(m));
+                base = __shfl_sync(full, base, __ffs(m) - 1);
+                if (need) {
+                    I = base + __popc(m & ((1u << lane) - 1u));
+                    if (I < d.nline) { load_branch(d, z, I, major, col, L); branch::begin(L, T); }
+                    else {
+                        L.phase = branch::DONE;
+                        if (d.count_work > 1 && !saw_empty) {
+                            saw_empty = true;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                            atomicMin(&d.counters->t[1], t_now);
+                        }
+                    }
+                }
+            }
+            double xl[6], xu[6];
+            load_bounds(col, xl, xu);
+            if (branch::eval_pass(L, eval, pass, xl, xu, max_auglag, mu_max, T)) {
+                store_branch(d, I, L);
+                work[0] += 1; work[1] += L.it_al; work[2] += L.evals; work[3] += L.cg; work[4] += L.shifts;
+                work[5] += L.rejected; work[6] += L.hit_max;
+                mx = max(mx, L.evals);
+                L.phase = branch::NEED;
+            }
         }
-        branch::Objective obj{ D, { d.als[I], d.als[nl + I] },
-                               (major == 1) ? 10.0 : d.als[2 * nl + I],      // auglag_gpu.jl:75-80
-                               scale };
-        double F[4];
-        branch::solve(obj, xl, xu, x, max_auglag, mu_max, T, F, wk);
-        d4 of, ot;
-        of.p = F[0]; of.q = F[1]; of.w = x[0] * x[0]; of.t = x[2];
-        ot.p = F[2]; ot.q = F[3]; ot.w = x[1] * x[1]; ot.t = x[3];
-        st4(d.u + d.gpad, sf, of);
-        st4(d.u + d.gpad, st, ot);
-        d.als[I] = obj.ls[0]; d.als[nl + I] = obj.ls[1]; d.als[2 * nl + I] = obj.mu;
+        if (__all_sync(full, L.phase == branch::DONE || L.phase == branch::NEED)) {
+            // NEED here means "finished in pass 1" cannot happen (pass 1 never finishes); lanes that finished in
+            // pass 0 were refilled or retired at the top of pass 1, so all lanes are DONE.
+            if (__all_sync(full, L.phase == branch::DONE)) break;
+        }
+        double xl[6], xu[6];
+        load_bounds(col, xl, xu);
+        branch::compute(L, xl, xu);
+    }
+
+    if (d.count_work > 1 && lane == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+        atomicMax(&d.counters->t[2], t_now);
     }
     if (d.count_work) {
-        // per-warp totals -> one atomic per counter per warp
-        unsigned long long vals[7] = { active ? 1ull : 0ull, (unsigned long long)wk.auglag, (unsigned long long)wk.evals,
-                                       (unsigned long long)wk.cg, (unsigned long long)wk.shifts,
-                                       (unsigned long long)wk.rejected, (unsigned long long)wk.hit_max };
-        int mx = wk.evals;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-            for (int k = 0; k < 7; ++k) vals[k] += __shfl_down_sync(0xffffffffu, vals[k], o);
-            mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+            for (int k = 0; k < 7; ++k) work[k] += __shfl_down_sync(full, work[k], o);
+            mx = max(mx, __shfl_down_sync(full, mx, o));
         }
-        if ((threadIdx.x & 31) == 0) {
+        if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 7; ++k) if (vals[k]) atomicAdd(&d.counters->v[k], vals[k]);
+            for (int k = 0; k < 7; ++k) if (work[k]) atomicAdd(&d.counters->v[k], work[k]);
             atomicMax(&d.counters->v[7], (unsigned long long)mx);
         }
     }
@@ -404,6 +483,7 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
             const long long inner = c->inner + 1;
             c->inner = inner;
             c->zsel = zsel ^ 1;
+            c->next_line = 0;
             // admm_two_level.jl:60-62 and the `while inner < inner_iterlim` bound (:34)
             if (c->res[0] <= c->eps_pri || inner >= c->inner_limit) c->done = 1;
         }
@@ -483,7 +563,7 @@ __global__ void k_membuf_row(Dev d, int zsel, int row, double *out) {
 
 __global__ void k_ctrl_begin(Ctrl *c, double beta, double eps_pri, long long inner0, long long inner_limit, int zsel) {
     c->beta = beta; c->eps_pri = eps_pri; c->inner = inner0; c->inner_limit = inner_limit;
-    c->done = 0; c->zsel = zsel; c->ticket = 0u;
+    c->done = 0; c->zsel = zsel; c->ticket = 0u; c->next_line = 0;
 }
 
 // diagnostics: evaluate f, g, H for a batch of points (unit parity vs the oracle)
@@ -500,7 +580,7 @@ __global__ void k_diag_eval(int n, const double *x, const double *param, const d
 #pragma unroll
     for (int k = 0; k < 6; ++k) xx[k] = x[6 * (size_t)i + k];
     branch::Sym6 A;
-    branch::eval_fgh(D, ls, p[26], scale, xx, ff, gg, A, F);
+    branch::eval_fgh(branch::StructView{ &D }, ls, p[26], scale, xx, ff, gg, A, F);
     f[i] = ff;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {

@@ -26,20 +26,76 @@
 #ifndef EA_DEV
 #define EA_DEV __host__ __device__ __forceinline__
 #endif
-// EA_NO_FMA (host test harness only) replaces every fused multiply-add by the
-// separately rounded a*b + c, which makes the arithmetic bit-identical to the
-// oracle's (compiled with -ffp-contract=off) so that logic can be compared exactly.
+// EA_NO_FMA (host test harness only) selects "exact" arithmetic: every fused
+// multiply-add becomes the separately rounded a*b + c and the triangular solves /
+// Cholesky keep true divisions and sqrt, which makes the arithmetic bit-identical
+// to the oracle's (compiled with -ffp-contract=off), so the control logic can be
+// compared exactly. The device build uses FMA and reciprocal / rsqrt forms
+// (fewer instructions on the critical path, results equal to within rounding).
 #ifdef EA_NO_FMA
 #define EA_FMA(a, b, c) ((a) * (b) + (c))
+#define EA_EXACT 1
 #else
 #define EA_FMA(a, b, c) fma((a), (b), (c))
+#ifdef EA_EXACT_DIV
+#define EA_EXACT 1
+#else
+#define EA_EXACT 0
+#endif
 #endif
 
 namespace tron {
 
+// ---- scalar helpers ------------------------------------------------------------------
+// min / max without the NaN bookkeeping of fmin / fmax (inputs are finite)
+EA_DEV double dmin(double a, double b) { return a < b ? a : b; }
+EA_DEV double dmax(double a, double b) { return a > b ? a : b; }
+
+// Division, reciprocal square root and square root. The device build uses the hardware
+// approximations refined by Newton steps (full double precision to within an ulp, no
+// slow-path branches: operands here are finite, normal and of the right sign by
+// construction); EA_EXACT and the host use the correctly rounded operations.
+EA_DEV double ddiv(double a, double b) {
+#if defined(__CUDA_ARCH__) && !EA_EXACT
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(fma(-b, r, 1.0), r, r);
+    r = fma(fma(-b, r, 1.0), r, r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+#else
+    return a / b;
+#endif
+}
+EA_DEV double drsqrt(double a) {            // a > 0
+#if defined(__CUDA_ARCH__) && !EA_EXACT
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    const double h = 0.5 * a;
+    r = fma(fma(-h * r, r, 0.5), r, r);
+    r = fma(fma(-h * r, r, 0.5), r, r);
+    return r;
+#else
+    return 1.0 / sqrt(a);
+#endif
+}
+EA_DEV double dsqrt(double a) {             // a >= 0
+#if defined(__CUDA_ARCH__) && !EA_EXACT
+    if (!(a > 0.0)) return 0.0;
+    const double r = drsqrt(a);
+    const double s = a * r;
+    return fma(fma(-s, s, a), 0.5 * r, s);
+#else
+    return sqrt(a);
+#endif
+}
+
 __host__ __device__ constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
 template <int N> struct Sym { double a[N * (N + 1) / 2]; };   // packed lower triangle
+// Cholesky factor: packed lower triangle + reciprocal diagonal (so that the many
+// triangular solves multiply instead of divide)
+template <int N> struct Chol { double a[N * (N + 1) / 2]; double rd[N]; };
 
 template <int N> EA_DEV double dot(const double (&x)[N], const double (&y)[N]) {
     double s = 0.0;
@@ -47,7 +103,7 @@ template <int N> EA_DEV double dot(const double (&x)[N], const double (&y)[N]) {
     for (int i = 0; i < N; ++i) s = EA_FMA(x[i], y[i], s);
     return s;
 }
-template <int N> EA_DEV double nrm2(const double (&x)[N]) { return sqrt(dot<N>(x, x)); }
+template <int N> EA_DEV double nrm2(const double (&x)[N]) { return dsqrt(dot<N>(x, x)); }
 
 // y = A x  (A packed symmetric)
 template <int N> EA_DEV void symv(const Sym<N> &A, const double (&x)[N], double (&y)[N]) {
@@ -62,7 +118,7 @@ template <int N> EA_DEV void symv(const Sym<N> &A, const double (&x)[N], double 
 
 template <int N> EA_DEV void mid(double (&x)[N], const double (&xl)[N], const double (&xu)[N]) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = fmax(xl[i], fmin(x[i], xu[i]));
+    for (int i = 0; i < N; ++i) x[i] = dmax(xl[i], dmin(x[i], xu[i]));
 }
 
 // s = P[x + alpha*w] - x   (Appendix B.1 dgpstep)
@@ -87,9 +143,9 @@ template <int N> EA_DEV void breakpt(const double (&x)[N], const double (&xl)[N]
         const bool up = (x[i] < xu[i]) && (wi > 0.0);
         const bool dn = (x[i] > xl[i]) && (wi < 0.0);
         if (up || dn) {
-            const double b = ((up ? xu[i] : xl[i]) - x[i]) / wi;
-            brptmin = any ? fmin(brptmin, b) : b;
-            brptmax = any ? fmax(brptmax, b) : b;
+            const double b = ddiv((up ? xu[i] : xl[i]) - x[i], wi);
+            brptmin = any ? dmin(brptmin, b) : b;
+            brptmax = any ? dmax(brptmax, b) : b;
             any = true;
         }
     }
@@ -102,10 +158,10 @@ template <int N> EA_DEV double gpnorm(const double (&x)[N], const double (&xl)[N
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         double v;
-        if (x[i] == xl[i]) v = fabs(fmin(g[i], 0.0));
-        else if (x[i] == xu[i]) v = fabs(fmax(g[i], 0.0));
+        if (x[i] == xl[i]) v = fabs(dmin(g[i], 0.0));
+        else if (x[i] == xu[i]) v = fabs(dmax(g[i], 0.0));
         else v = fabs(g[i]);
-        if (xl[i] != xu[i]) nrm = fmax(nrm, v);
+        if (xl[i] != xu[i]) nrm = dmax(nrm, v);
     }
     return nrm;
 }
@@ -114,9 +170,9 @@ template <int N> EA_DEV double gpnorm(const double (&x)[N], const double (&xl)[N
 template <int N> EA_DEV double trqsol(const double (&x)[N], const double (&p)[N], double delta) {
     const double ptx = dot<N>(p, x), ptp = dot<N>(p, p), xtx = dot<N>(x, x);
     const double dsq = delta * delta;
-    const double rad = sqrt(fmax(EA_FMA(ptx, ptx, ptp * (dsq - xtx)), 0.0));
-    if (ptx > 0.0) return (dsq - xtx) / (ptx + rad);
-    if (rad > 0.0) return (rad - ptx) / ptp;
+    const double rad = dsqrt(dmax(EA_FMA(ptx, ptx, ptp * (dsq - xtx)), 0.0));
+    if (ptx > 0.0) return ddiv(dsq - xtx, ptx + rad);
+    if (rad > 0.0) return ddiv(rad - ptx, ptp);
     return 0.0;
 }
 
@@ -129,65 +185,76 @@ template <int N> EA_DEV void quad(const Sym<N> &A, const double (&g)[N], const d
     q = EA_FMA(0.5, dot<N>(s, w), gts);
 }
 
-// Cauchy step (B.2 dcauchy). Returns the new alpha; s is the step.
+// Cauchy step (B.2 dcauchy). Returns the new alpha; s is the step. One loop with a
+// single projected-step / quadratic-model site (the three phases of the original:
+// first trial, interpolation, extrapolation) to keep the instruction footprint small.
 template <int N> EA_DEV double cauchy(const double (&x)[N], const double (&xl)[N], const double (&xu)[N],
                                                           const Sym<N> &A, const double (&g)[N], double delta,
                                                           double alpha, double (&s)[N]) {
     const double mu0 = 0.01, interpf = 0.1, extrapf = 10.0;
-    double brptmin, brptmax, q, gts;
+    double brptmin, brptmax;
     breakpt<N>(x, xl, xu, g, -1.0, brptmin, brptmax);
-    gpstep<N>(x, xl, xu, -alpha, g, s);
-    bool interp;
-    if (nrm2<N>(s) > delta) interp = true;
-    else { quad<N>(A, g, s, q, gts); interp = (q >= mu0 * gts); }
-    if (interp) {
-        bool search = true;
+    int mode = 0;                 // 0 first trial, 1 interpolating, 2 extrapolating, 3 recover last good, 4 done
+    double alphas = alpha;
 #pragma unroll 1
-        while (search) {
-            alpha = interpf * alpha;
-            gpstep<N>(x, xl, xu, -alpha, g, s);
-            if (nrm2<N>(s) <= delta) { quad<N>(A, g, s, q, gts); search = (q > mu0 * gts); }
-        }
-    } else {
-        bool search = true;
-        double alphas = alpha;
-#pragma unroll 1
-        while (search && alpha <= brptmax) {
-            alpha = extrapf * alpha;
-            gpstep<N>(x, xl, xu, -alpha, g, s);
-            if (nrm2<N>(s) <= delta) {
-                quad<N>(A, g, s, q, gts);
-                if (q < mu0 * gts) { search = true; alphas = alpha; }
-            } else search = false;
-        }
-        alpha = alphas;
+    while (mode != 4) {
         gpstep<N>(x, xl, xu, -alpha, g, s);
+        if (mode == 3) break;
+        const bool within = nrm2<N>(s) <= delta;
+        double q = 0.0, gts = 0.0;
+        if (within) quad<N>(A, g, s, q, gts);
+        if (mode == 0) {
+            const bool interp = !within || (q >= mu0 * gts);
+            if (interp) { mode = 1; alpha = interpf * alpha; }
+            else {
+                alphas = alpha;
+                if (alpha <= brptmax) { mode = 2; alpha = extrapf * alpha; }
+                else mode = 3;                                   // loop body of the original never runs
+            }
+        } else if (mode == 1) {
+            if (within && !(q > mu0 * gts)) mode = 4;
+            else alpha = interpf * alpha;
+        } else {                                                 // mode 2
+            bool search = true;
+            if (within) { if (q < mu0 * gts) alphas = alpha; }
+            else search = false;
+            if (search && alpha <= brptmax) alpha = extrapf * alpha;
+            else { alpha = alphas; mode = 3; }
+        }
     }
     return alpha;
 }
 
 // Lower-triangular solves with the free-set mask folded into L (fixed rows are e_i).
-template <int N> EA_DEV void lsolve(const Sym<N> &L, double (&r)[N]) {      // L r = b
+template <int N> EA_DEV void lsolve(const Chol<N> &L, double (&r)[N]) {      // L r = b
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         double s = r[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) s = EA_FMA(-L.a[tri(i, k)], r[k], s);
+#if EA_EXACT
         r[i] = s / L.a[tri(i, i)];
+#else
+        r[i] = s * L.rd[i];
+#endif
     }
 }
-template <int N> EA_DEV void ltsolve(const Sym<N> &L, double (&r)[N]) {     // L' r = b
+template <int N> EA_DEV void ltsolve(const Chol<N> &L, double (&r)[N]) {     // L' r = b
 #pragma unroll
     for (int i = N - 1; i >= 0; --i) {
         double s = r[i];
 #pragma unroll
         for (int k = i + 1; k < N; ++k) s = EA_FMA(-L.a[tri(k, i)], r[k], s);
+#if EA_EXACT
         r[i] = s / L.a[tri(i, i)];
+#else
+        r[i] = s * L.rd[i];
+#endif
     }
 }
 
 // In-place dense Cholesky of the packed lower triangle; false if a pivot is <= 0.
-template <int N> EA_DEV bool cholesky(Sym<N> &L) {
+template <int N> EA_DEV bool cholesky(Chol<N> &L) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
@@ -195,6 +262,7 @@ template <int N> EA_DEV bool cholesky(Sym<N> &L) {
 #pragma unroll
         for (int k = 0; k < j; ++k) d = EA_FMA(-L.a[tri(j, k)], L.a[tri(j, k)], d);
         ok = ok && (d > 0.0);
+#if EA_EXACT
         d = sqrt(d);
         L.a[tri(j, j)] = d;
 #pragma unroll
@@ -204,39 +272,49 @@ template <int N> EA_DEV bool cholesky(Sym<N> &L) {
             for (int k = 0; k < j; ++k) s = EA_FMA(-L.a[tri(i, k)], L.a[tri(j, k)], s);
             L.a[tri(i, j)] = s / d;
         }
+#else
+        const double r = drsqrt(d);
+        L.a[tri(j, j)] = d * r;
+        L.rd[j] = r;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            double s = L.a[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = EA_FMA(-L.a[tri(i, k)], L.a[tri(j, k)], s);
+            L.a[tri(i, j)] = s * r;
+        }
+#endif
     }
     return ok;
 }
 
-// B.5 dicfs for a dense matrix: scaled Cholesky of the masked matrix with the
-// shift search. Returns true if a diagonal shift was needed.
-template <int N> EA_DEV bool icfs(const Sym<N> &A, unsigned freemask, Sym<N> &L) {
+// B.5 dicfs for a dense matrix: scaled Cholesky of the masked matrix with the shift
+// search; the general algorithm (non-positive diagonal, failed pivots, shifts). Kept
+// out of line: it runs for a handful of factorizations per million.
+template <int N> __host__ __device__ __noinline__ void icfs_general(const Sym<N> &A, unsigned freemask, Chol<N> &L) {
     const double alpham = 1e-3, nbfactor = 512.0;
     const int nbmax = 3;
-    double wa2[N];
+    double wa2[N];        // the scaling D = diag(1/sqrt(a_ii))
     double alphas = alpham, alpha = 0.0;
-    bool needcol = false;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const bool fr = (freemask >> i) & 1u;
         const double aii = A.a[tri(i, i)];
-        if (fr && !(aii > 0.0)) needcol = true;
-        wa2[i] = fr ? 1.0 / sqrt(aii) : 1.0;  // aii <= 0 is repaired just below
-    }
-    if (needcol) {                            // rare: non-positive diagonal entry
+        wa2[i] = 1.0;
+        if (fr && aii > 0.0) {
+#if EA_EXACT
+            wa2[i] = 1.0 / sqrt(aii);
+#else
+            wa2[i] = drsqrt(aii);
+#endif
+        } else if (fr) {                       // non-positive diagonal entry: scale by the column norm
+            double cs = 0.0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const bool fr = (freemask >> i) & 1u;
-            const double aii = A.a[tri(i, i)];
-            if (fr && !(aii > 0.0)) {
-                double cs = 0.0;
-#pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    const double akj = ((freemask >> k) & 1u) ? A.a[tri(k, i)] : 0.0;
-                    cs = EA_FMA(akj, akj, cs);
-                }
-                wa2[i] = 1.0 / sqrt(sqrt(cs));
+            for (int k = 0; k < N; ++k) {
+                const double akj = ((freemask >> k) & 1u) ? A.a[tri(k, i)] : 0.0;
+                cs = EA_FMA(akj, akj, cs);
             }
+            wa2[i] = 1.0 / sqrt(sqrt(cs));
         }
     }
 #pragma unroll
@@ -244,11 +322,10 @@ template <int N> EA_DEV bool icfs(const Sym<N> &A, unsigned freemask, Sym<N> &L)
         if ((freemask >> i) & 1u) {
             const double aii = A.a[tri(i, i)];
             if (aii == 0.0) alpha = alphas;
-            else alpha = fmax(alpha, -aii * (wa2[i] * wa2[i]));
+            else alpha = dmax(alpha, -aii * (wa2[i] * wa2[i]));
         }
     }
-    if (alpha > 0.0) alpha = fmax(alpha, alphas);
-    const bool shifted = alpha > 0.0;
+    if (alpha > 0.0) alpha = dmax(alpha, alphas);
     int nb = 1;
 #pragma unroll 1
     for (;;) {
@@ -267,20 +344,75 @@ template <int N> EA_DEV bool icfs(const Sym<N> &A, unsigned freemask, Sym<N> &L)
         if (cholesky<N>(L)) {
             if (alpha == alphas && nb < nbmax) { alphas = alphas / nbfactor; alpha = alphas; nb++; }
             else {
+                // undo the scaling: L <- D^-1 L
 #pragma unroll
-                for (int i = 0; i < N; ++i)
+                for (int i = 0; i < N; ++i) {
 #pragma unroll
                     for (int j = 0; j <= i; ++j) L.a[tri(i, j)] = L.a[tri(i, j)] / wa2[i];
+                    L.rd[i] = L.rd[i] * wa2[i];
+                }
                 break;
             }
-        } else alpha = fmax(2.0 * alpha, alphas);
+        } else alpha = dmax(2.0 * alpha, alphas);
     }
-    return shifted;
+}
+
+// dicfs, common case first: every free diagonal entry is positive and the unshifted
+// factorization succeeds (then the general algorithm does exactly this single attempt).
+// Returns true if the general path (shift search) had to run.
+template <int N> EA_DEV bool icfs(const Sym<N> &A, unsigned freemask, Chol<N> &L) {
+    double wa2[N];
+    bool pos = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const bool fr = (freemask >> i) & 1u;
+        const double aii = A.a[tri(i, i)];
+        pos = pos && (!fr || aii > 0.0);
+#if EA_EXACT
+        wa2[i] = fr ? 1.0 / sqrt(aii) : 1.0;
+#else
+        wa2[i] = fr ? drsqrt(aii) : 1.0;
+#endif
+    }
+    if (pos) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool fi = (freemask >> i) & 1u;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const bool fj = (freemask >> j) & 1u;
+                L.a[tri(i, j)] = (fi && fj) ? A.a[tri(i, j)] * wa2[i] * wa2[j] + 0.0 : ((i == j) ? 1.0 : 0.0);
+            }
+        }
+        if (cholesky<N>(L)) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#if EA_EXACT
+#pragma unroll
+                for (int j = 0; j <= i; ++j) L.a[tri(i, j)] = L.a[tri(i, j)] / wa2[i];
+#else
+                const bool fi = (freemask >> i) & 1u;
+                const double si = fi ? A.a[tri(i, i)] * wa2[i] : 1.0;     // sqrt(a_ii) = a_ii * rsqrt(a_ii)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) L.a[tri(i, j)] = L.a[tri(i, j)] * si;
+                L.rd[i] = L.rd[i] * wa2[i];
+#endif
+            }
+            return false;
+        }
+    }
+    {   // rare: go through addressable copies so that A and L themselves stay in registers
+        Sym<N> A2 = A;
+        Chol<N> L2;
+        icfs_general<N>(A2, freemask, L2);
+        L = L2;
+    }
+    return true;
 }
 
 // B.4 dtrpcg on the masked system. w is the solution in the L-transformed space.
 template <int N> EA_DEV void trpcg(const Sym<N> &A, unsigned freemask, const double (&g)[N], double delta,
-                                                       const Sym<N> &L, double tol, double stol, int itermax,
+                                                       const Chol<N> &L, double tol, double stol, int itermax,
                                                        double (&w)[N], int &iters, int &info) {
     double t[N], r[N], p[N], q[N], z[N];
 #pragma unroll
@@ -289,7 +421,7 @@ template <int N> EA_DEV void trpcg(const Sym<N> &A, unsigned freemask, const dou
 #pragma unroll
     for (int i = 0; i < N; ++i) p[i] = r[i];
     double rho = dot<N>(r, r);
-    if (sqrt(rho) == 0.0) { iters = 0; info = 1; return; }
+    if (rho == 0.0) { iters = 0; info = 1; return; }
     iters = itermax; info = 5;
 #pragma unroll 1
     for (int it = 1; it <= itermax; ++it) {
@@ -301,7 +433,7 @@ template <int N> EA_DEV void trpcg(const Sym<N> &A, unsigned freemask, const dou
         for (int i = 0; i < N; ++i) { q[i] = ((freemask >> i) & 1u) ? q[i] : 0.0; z[i] = q[i]; }
         lsolve<N>(L, q);
         const double ptq = dot<N>(p, q);
-        const double alpha = (ptq > 0.0) ? rho / ptq : 0.0;
+        const double alpha = (ptq > 0.0) ? ddiv(rho, ptq) : 0.0;
         const double sigma = trqsol<N>(w, p, delta);
         if (ptq <= 0.0 || alpha >= sigma) {
 #pragma unroll
@@ -313,8 +445,8 @@ template <int N> EA_DEV void trpcg(const Sym<N> &A, unsigned freemask, const dou
         for (int i = 0; i < N; ++i) { w[i] = EA_FMA(alpha, p[i], w[i]); r[i] = EA_FMA(-alpha, q[i], r[i]); t[i] = EA_FMA(-alpha, z[i], t[i]); }
         const double rtr = dot<N>(r, r);
         if (nrm2<N>(t) <= tol) { iters = it; info = 1; return; }
-        if (sqrt(rtr) <= stol) { iters = it; info = 2; return; }
-        const double beta = rtr / rho;
+        if (dsqrt(rtr) <= stol) { iters = it; info = 2; return; }
+        const double beta = ddiv(rtr, rho);
 #pragma unroll
         for (int i = 0; i < N; ++i) p[i] = EA_FMA(beta, p[i], r[i]);
         rho = rtr;
@@ -363,7 +495,7 @@ template <int N> EA_DEV void spcg(double (&x)[N], const double (&xl)[N], const d
         for (int j = 0; j < N; ++j)
             if (xl[j] < x[j] && x[j] < xu[j]) freemask |= (1u << j);
         if (freemask == 0) return;
-        Sym<N> L;
+        Chol<N> L;
         if (icfs<N>(A, freemask, L)) st.shifts++;
         double gfree[N], wf[N];
         double gsq = 0.0;
@@ -374,7 +506,7 @@ template <int N> EA_DEV void spcg(double (&x)[N], const double (&xl)[N], const d
             const double gj = fr ? g[j] : 0.0;
             gsq = EA_FMA(gj, gj, gsq);
         }
-        const double gfnorm = sqrt(gsq);
+        const double gfnorm = dsqrt(gsq);
         int itertr, infotr;
         trpcg<N>(A, freemask, gfree, delta, L, rtol * gfnorm, 0.0, itermax, wf, itertr, infotr);
         iters += itertr;
@@ -390,7 +522,7 @@ template <int N> EA_DEV void spcg(double (&x)[N], const double (&xl)[N], const d
             const double v = ((freemask >> j) & 1u) ? (w[j] + g[j]) : 0.0;
             gf2 = EA_FMA(v, v, gf2);
         }
-        if (sqrt(gf2) <= rtol * gfnorm) return;
+        if (dsqrt(gf2) <= rtol * gfnorm) return;
         if (infotr == 3 || infotr == 4) return;
         if (iters > itermax) return;
     }
@@ -420,13 +552,13 @@ EA_DEV int judge_step(double f_trial, double fc, double g0, double snorm, double
     const double eta0 = 1e-4, eta1 = 0.25, eta2 = 0.75, sigma1 = 0.25, sigma2 = 0.5, sigma3 = 4.0;
     const double frtol = 1e-12, fatol = 0.0, fmin_ = -1e32;
     const double actred = fc - f_trial;
-    if (first_iter) delta = fmin(delta, snorm);
+    if (first_iter) delta = dmin(delta, snorm);
     const double den = f_trial - fc - g0;
-    const double alpha = (den <= 0.0) ? sigma3 : fmax(sigma1, -0.5 * (g0 / den));
-    if (actred < eta0 * prered) delta = fmin(fmax(alpha, sigma1) * snorm, sigma2 * delta);
-    else if (actred < eta1 * prered) delta = fmax(sigma1 * delta, fmin(alpha * snorm, sigma2 * delta));
-    else if (actred < eta2 * prered) delta = fmax(sigma1 * delta, fmin(alpha * snorm, sigma3 * delta));
-    else delta = fmax(delta, fmin(alpha * snorm, sigma3 * delta));
+    const double alpha = (den <= 0.0) ? sigma3 : dmax(sigma1, -0.5 * ddiv(g0, den));
+    if (actred < eta0 * prered) delta = dmin(dmax(alpha, sigma1) * snorm, sigma2 * delta);
+    else if (actred < eta1 * prered) delta = dmax(sigma1 * delta, dmin(alpha * snorm, sigma2 * delta));
+    else if (actred < eta2 * prered) delta = dmax(sigma1 * delta, dmin(alpha * snorm, sigma3 * delta));
+    else delta = dmax(delta, dmin(alpha * snorm, sigma3 * delta));
     accepted = actred > eta0 * prered;
     const double f = accepted ? f_trial : fc;
     int task = accepted ? 1 : 0;

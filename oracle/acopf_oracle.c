@@ -37,6 +37,7 @@ struct orc_model {
     double *membuf;
     int nthreads;
     ea_counters_t cnt;
+    int32_t *eval_trace;   /* optional: per-line evaluation count of the last x-update (diagnostics) */
 };
 
 /* ------------------------------------------------------------------------ */
@@ -591,6 +592,7 @@ void orc_set_pg_bounds(orc_model_t *m, const double *lo, const double *hi) {
 }
 void orc_get_counters(const orc_model_t *m, ea_counters_t *out) { *out = m->cnt; }
 void orc_reset_counters(orc_model_t *m) { memset(&m->cnt, 0, sizeof(m->cnt)); }
+void orc_set_eval_trace(orc_model_t *m, int32_t *buf) { m->eval_trace = buf; }
 
 /* acopf_init_solution_cpu.jl:1-45 */
 void orc_init_solution(orc_model_t *m, double rho_pq, double rho_va) {
@@ -715,6 +717,7 @@ static void solve_branch(orc_model_t *m, int64_t I, int64_t major_iter, int32_t 
     cnt->chol_shifts += st.shifts;
     cnt->rejected_steps += st.rejected;
     if (st.nfev > cnt->max_evals_lane) cnt->max_evals_lane = st.nfev;
+    if (m->eval_trace) m->eval_trace[I] = (int32_t)st.nfev;
 }
 
 static void merge_counters(ea_counters_t *dst, const ea_counters_t *src) {

@@ -51,6 +51,8 @@ void    orc_set_load(orc_model_t *m, const double *Pd, const double *Qd);
 void    orc_set_pg_bounds(orc_model_t *m, const double *lo, const double *hi);
 void    orc_get_counters(const orc_model_t *m, ea_counters_t *out);
 void    orc_reset_counters(orc_model_t *m);
+/* diagnostics: buf[nline] receives the per-line evaluation count of every x-update (NULL = off) */
+void    orc_set_eval_trace(orc_model_t *m, int32_t *buf);
 
 /* Unit-level entry points used by the tests.
  * param = one membuf column (31 doubles, 0-based index k <-> reference row k+1);

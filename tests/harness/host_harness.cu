@@ -6,44 +6,26 @@
 #include <cmath>
 #include <cstring>
 
-extern "C" {
-
-// param: 31 doubles (membuf column, 0-based rows); rows 24-26 (lambda_s, mu) updated in place.
-// x: 6 doubles in/out. Y: 8. xl/xu: 6. work[6]: auglag, evals, cg, shifts, rejected, hit_max.
-void hh_solve_branch(double *x, const double *xl, const double *xu, double *param, const double *Y,
-                     long long major_iter, int max_auglag, double mu_max, double scale, double *F, int *work) {
-    branch::Data D;
-    for (int k = 0; k < 8; ++k) { D.lam[k] = param[k]; D.rho[k] = param[8 + k]; D.xt[k] = param[16 + k]; D.Y[k] = Y[k]; }
-    double ls[2] = { param[24], param[25] };
-    double mu = (major_iter == 1) ? 10.0 : param[26];
-    branch::PowTable T; T.n = 0;
+static void make_pow_table(branch::PowTable &T, double mu_max) {
+    T.n = 0;
     double m = 10.0;
     for (int k = 0; k < 24; ++k) {
         T.mu[k] = m; T.inv_p01[k] = 1.0 / std::pow(m, 0.1); T.p09[k] = std::pow(m, 0.9); T.n = k + 1;
         double nx = std::fmin(mu_max, m * 10); if (nx == m) break; m = nx;
     }
-    double xx[6], l[6], u[6], FF[4];
-    for (int k = 0; k < 6; ++k) { xx[k] = x[k]; l[k] = xl[k]; u[k] = xu[k]; }
-    branch::Work wk;
-    branch::Objective obj{ D, { ls[0], ls[1] }, mu, scale };
-    branch::solve(obj, l, u, xx, max_auglag, mu_max, T, FF, wk);
-    for (int k = 0; k < 6; ++k) x[k] = xx[k];
-    for (int k = 0; k < 4; ++k) F[k] = FF[k];
-    param[24] = obj.ls[0]; param[25] = obj.ls[1]; param[26] = obj.mu;
-    work[0] = wk.auglag; work[1] = wk.evals; work[2] = wk.cg; work[3] = wk.shifts; work[4] = wk.rejected; work[5] = wk.hit_max;
 }
 
-// The same flattened AL/TRON loop, but with the ORACLE's f / grad / Hessian plugged in
+// The ORACLE's f / grad / Hessian plugged into the product's state machine
 // (function pointers into oracle/_build/libacopf_oracle.so). Built with -DEA_NO_FMA the
 // arithmetic of the TRON routines is then bit-identical to the oracle's restatement, so
 // iterates and evaluation counts must match EXACTLY - any difference is a logic error.
 typedef double (*orc_f_t)(const double *, const double *, const double *, double);
 typedef void (*orc_gh_t)(const double *, const double *, const double *, double, double *, double *);
 
-struct OracleObjective {
+struct OracleEval {
     orc_f_t fn; orc_gh_t ghn; double *param; const double *Y; double scale;
-    double ls[2]; double mu;
-    void eval(const double (&x)[6], double &f, double (&g)[6], branch::Sym6 &A, double (&F)[4]) {
+    void operator()(const double (&x)[6], const double (&ls)[2], double mu, double &f, double (&g)[6],
+                    branch::Sym6 &A, double (&F)[4]) const {
         param[24] = ls[0]; param[25] = ls[1]; param[26] = mu;
         double H[36];
         f = fn(x, param, Y, scale);
@@ -57,24 +39,40 @@ struct OracleObjective {
     }
 };
 
+template <class Eval>
+static void run(const Eval &eval, double *x, const double *xl, const double *xu, double *param, long long major_iter,
+                int max_auglag, double mu_max, double *F, int *work) {
+    branch::PowTable T;
+    make_pow_table(T, mu_max);
+    branch::Lane L;
+    double l[6], u[6];
+    for (int k = 0; k < 6; ++k) { L.x[k] = x[k]; l[k] = xl[k]; u[k] = xu[k]; }
+    L.ls[0] = param[24]; L.ls[1] = param[25];
+    L.mu = (major_iter == 1) ? 10.0 : param[26];
+    branch::solve(L, eval, l, u, max_auglag, mu_max, T);
+    for (int k = 0; k < 6; ++k) x[k] = L.x[k];
+    if (F) for (int k = 0; k < 4; ++k) F[k] = L.Fc[k];
+    param[24] = L.ls[0]; param[25] = L.ls[1]; param[26] = L.mu;
+    work[0] = L.it_al; work[1] = L.evals; work[2] = L.cg; work[3] = L.shifts; work[4] = L.rejected; work[5] = L.hit_max;
+}
+
+extern "C" {
+
+// param: 31 doubles (membuf column, 0-based rows); rows 24-26 (lambda_s, mu) updated in place.
+// x: 6 doubles in/out. Y: 8. xl/xu: 6. work[6]: auglag, evals, cg, shifts, rejected, hit_max.
+void hh_solve_branch(double *x, const double *xl, const double *xu, double *param, const double *Y,
+                     long long major_iter, int max_auglag, double mu_max, double scale, double *F, int *work) {
+    branch::Data D;
+    for (int k = 0; k < 8; ++k) { D.lam[k] = param[k]; D.rho[k] = param[8 + k]; D.xt[k] = param[16 + k]; D.Y[k] = Y[k]; }
+    const branch::Objective<branch::StructView> eval{ { &D }, scale };
+    run(eval, x, xl, xu, param, major_iter, max_auglag, mu_max, F, work);
+}
+
 void hh_solve_branch_oracle_eval(void *fn, void *ghn, double *x, const double *xl, const double *xu, double *param,
                                  const double *Y, long long major_iter, int max_auglag, double mu_max, double scale,
                                  int *work) {
-    branch::PowTable T; T.n = 0;
-    double m = 10.0;
-    for (int k = 0; k < 24; ++k) {
-        T.mu[k] = m; T.inv_p01[k] = 1.0 / std::pow(m, 0.1); T.p09[k] = std::pow(m, 0.9); T.n = k + 1;
-        double nx = std::fmin(mu_max, m * 10); if (nx == m) break; m = nx;
-    }
-    OracleObjective obj{ (orc_f_t)fn, (orc_gh_t)ghn, param, Y, scale, { param[24], param[25] },
-                         (major_iter == 1) ? 10.0 : param[26] };
-    double xx[6], l[6], u[6], FF[4];
-    for (int k = 0; k < 6; ++k) { xx[k] = x[k]; l[k] = xl[k]; u[k] = xu[k]; }
-    branch::Work wk;
-    branch::solve(obj, l, u, xx, max_auglag, mu_max, T, FF, wk);
-    for (int k = 0; k < 6; ++k) x[k] = xx[k];
-    param[24] = obj.ls[0]; param[25] = obj.ls[1]; param[26] = obj.mu;
-    work[0] = wk.auglag; work[1] = wk.evals; work[2] = wk.cg; work[3] = wk.shifts; work[4] = wk.rejected; work[5] = wk.hit_max;
+    const OracleEval eval{ (orc_f_t)fn, (orc_gh_t)ghn, param, Y, scale };
+    run(eval, x, xl, xu, param, major_iter, max_auglag, mu_max, nullptr, work);
 }
 
 void hh_eval(const double *x, const double *param, const double *Y, double scale, double *f, double *g, double *H) {
@@ -83,7 +81,7 @@ void hh_eval(const double *x, const double *param, const double *Y, double scale
     double ls[2] = { param[24], param[25] }, xx[6], gg[6], F[4];
     for (int k = 0; k < 6; ++k) xx[k] = x[k];
     branch::Sym6 A;
-    branch::eval_fgh(D, ls, param[26], scale, xx, *f, gg, A, F);
+    branch::eval_fgh(branch::StructView{ &D }, ls, param[26], scale, xx, *f, gg, A, F);
     for (int a = 0; a < 6; ++a) { g[a] = gg[a]; for (int b = 0; b < 6; ++b) H[6 * a + b] = A.a[tron::tri(a, b)]; }
 }
 

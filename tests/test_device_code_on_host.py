@@ -116,15 +116,21 @@ def test_tron_logic_is_bit_identical_to_oracle_on_hard_problems(host_harness_nof
 
 
 def test_branch_solver_random_problems_fma_build(host_harness):
-    """The GPU-arithmetic build (FMA, fused compact objective) on well-conditioned random
-    problems: same evaluation counts, solutions within 1e-10."""
+    """The GPU-arithmetic build (FMA, rsqrt/reciprocal Cholesky, fused compact objective) on
+    random cold-start problems. A single TRON solve is only defined up to its own tolerances
+    (gtol, CG truncation), so rounding can change the path: require equally good solutions
+    everywhere and the identical path on the vast majority."""
     rng = np.random.default_rng(12)
+    same_path = total = 0
     for k in range(300):
         x0, xl, xu, p, Y = _random_problem(rng, binding=bool(k % 2))
         pc = p.copy(); xc = x0.copy()
         F = np.zeros(4); work = (C.c_int * 6)()
         host_harness.hh_solve_branch(P(xc), P(xl), P(xu), P(pc), P(Y), 2, 1, 1e8, 1e-4, P(F), work)   # one TRON solve
         xo, st, minor, nfev = orc.tron_solve(x0, xl, xu, p, Y, 1e-4)
-        if nfev < 30:                                      # long solves are roundoff-chaotic; covered exactly above
-            assert work[1] == nfev
-            np.testing.assert_allclose(xc, xo, rtol=0, atol=1e-10)
+        fd, fo = orc.eval_f(xc, p, Y, 1e-4), orc.eval_f(xo, p, Y, 1e-4)
+        assert abs(fd - fo) <= 1e-9 * max(1.0, abs(fo))
+        np.testing.assert_allclose(xc, xo, rtol=0, atol=1e-4)
+        total += 1
+        same_path += (work[1] == nfev) and np.allclose(xc, xo, rtol=0, atol=1e-10)
+    assert same_path >= 0.95 * total, (same_path, total)
