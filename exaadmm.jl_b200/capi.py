@@ -139,10 +139,19 @@ SIGNATURES = {
     "ea_set_membuf": (C.c_int, [_H, C.c_int, _pd, C.c_int64]),
     "ea_set_load": (C.c_int, [_H, _pd, _pd, C.c_int64]),
     "ea_set_pg_bounds": (C.c_int, [_H, _pd, _pd, C.c_int64]),
+    "ea_set_partition": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _pi, _pi, C.c_int64, _pi, _pi, _pi, _pi,
+                                   C.c_int64]),
+    "ea_nccl_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "ea_comm_init": (C.c_int, [_H, C.c_char_p, C.c_char_p]),
+    "ea_part_begin": (C.c_int, [_H, C.c_int64, C.c_double, C.c_int32, C.c_double, C.c_double]),
+    "ea_part_get_message": (C.c_int, [_H, _pd, C.c_int64]),
+    "ea_part_put_gathered": (C.c_int, [_H, _pd, C.c_int64]),
+    "ea_part_end": (C.c_int, [_H, _pd]),
     "ea_get_counters": (C.c_int, [_H, C.POINTER(EaCounters)]),
     "ea_reset_counters": (C.c_int, [_H]),
     "ea_set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
     "ea_get_kernel_times": (C.c_int, [_H, _pd]),
+    "ea_diag_fp64_peak": (C.c_int, [C.c_int, _pd]),
     "ea_diag_branch_eval": (C.c_int, [C.c_int, C.c_int64, _pd, _pd, _pd, C.c_double, _pd, _pd, _pd]),
 }
 

@@ -4,6 +4,9 @@
 #include "../../include/exaadmm_b200.h"
 #include "kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -52,10 +55,54 @@ struct ea_handle {
     long long n_x = 0, n_bus = 0, n_other = 0;  // kernels launched
     double t_x = 0.0, t_bus = 0.0;              // summed durations (kernel_timing only)
     int kernel_timing = 0;
+    int loopback = 0;                           // tests: exchange done by the caller through the host
     std::vector<cudaEvent_t> kev;               // event pool for kernel_timing
     cudaEvent_t span0 = nullptr, span1 = nullptr;
+    // bus-partitioned multi-GPU mode
+    int part_rank = 0, part_nranks = 1;
+    int64_t n_owned_entries = 0;                // prefix of the HBM layout owned by this rank
+    double *gather_dev = nullptr;               // nranks x stride
+    double *gather_host = nullptr;              // pinned mirror (scalar collectives, loopback tests)
+    ncclComm_t comm = nullptr;
+    void *nccl_lib = nullptr;
     std::string err;
 };
+
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    void *lib = nullptr;
+};
+NcclApi g_nccl;
+
+// NCCL is loaded at run time (dlopen) so that the library has no link-time dependency on it:
+// single-GPU users never touch it, and the process can share torch's bundled libnccl.
+const char *load_nccl(const char *path) {
+    if (g_nccl.lib) return nullptr;
+    const char *cands[] = { path, getenv("EXAADMM_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+    void *lib = nullptr;
+    for (const char *p : cands) {
+        if (!p || !*p) continue;
+        lib = dlopen(p, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return "cannot dlopen libnccl (pass its path or set EXAADMM_NCCL_LIB)";
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(lib, "ncclAllGather");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
+        return "libnccl is missing a required symbol";
+    g_nccl.lib = lib;
+    return nullptr;
+}
+}  // namespace
+
 
 namespace {
 
@@ -294,6 +341,8 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     if ((rc = dev_alloc(h, &h->res_dev, 4))) return bail(rc);
     if ((rc = dev_alloc(h, &h->staging, (size_t)std::max<int64_t>({ h->nvar, (int64_t)nline, (int64_t)nbus, (int64_t)ngen, 1 })))) return bail(rc);
     d.count_work = 1;
+    d.nbus_active = nbus;
+    h->n_owned_entries = nint;
     if (cudaMallocHost((void **)&h->ctrl_host, sizeof(Ctrl)) != cudaSuccess) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
     if (cudaMallocHost((void **)&h->res_host, 4 * sizeof(double)) != cudaSuccess) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
     memset(h->ctrl_host, 0, sizeof(Ctrl));
@@ -305,6 +354,8 @@ void ea_destroy(ea_handle_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->gather_host) cudaFreeHost(h->gather_host);
     for (void *p : h->allocs) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->res_host) cudaFreeHost(h->res_host);
@@ -330,14 +381,34 @@ int ea_init_solution(ea_handle_t *h, double rho_pq, double rho_va) {
     return EA_OK;
 }
 
+// Sum of one scalar over the ranks of a partitioned handle (rank order, identical on every rank).
+static int allgather_scalar_sum(ea_handle *h, double local, double *total) {
+    if (!h->d.partitioned) { *total = local; return EA_OK; }
+    if (!h->comm) return fail(h, EA_ERR_STATE, "partitioned handle without a communicator (call ea_comm_init)");
+    CK(cudaMemcpyAsync(h->d.sendbuf, &local, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    ncclResult_t r = g_nccl.AllGather(h->d.sendbuf, h->gather_dev, (size_t)h->d.stride, ncclDouble, h->comm, h->stream);
+    if (r != ncclSuccess) return fail(h, EA_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+    CK(cudaMemcpyAsync(h->gather_host, h->gather_dev, sizeof(double) * (size_t)h->d.stride * h->part_nranks, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    double s = 0.0;
+    for (int r2 = 0; r2 < h->part_nranks; ++r2) s += h->gather_host[(size_t)r2 * h->d.stride];
+    *total = s;
+    return EA_OK;
+}
+
 static int norm_of(ea_handle *h, const double *x, double *out) {
-    const int grid = std::min(h->max_blocks, nblocks(h->nint, RBLOCK));
-    k_norm<<<grid, RBLOCK, 0, h->stream>>>(h->nint, x, h->d.partials, &h->d.ctrl->ticket, h->res_dev);
+    const int n = (int)h->n_owned_entries;            // the whole vector, or this rank's owned prefix
+    const int grid = std::min(h->max_blocks, nblocks(n, RBLOCK));
+    k_norm<<<grid, RBLOCK, 0, h->stream>>>(n, x, h->d.partials, &h->d.ctrl->ticket, h->res_dev);
     CK(cudaGetLastError());
     h->n_other++;
     CK(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    *out = h->res_host[0];
+    if (!h->d.partitioned) { *out = h->res_host[0]; return EA_OK; }
+    double tot = 0.0;
+    int rc = allgather_scalar_sum(h, h->res_host[0] * h->res_host[0], &tot);
+    if (rc) return rc;
+    *out = std::sqrt(tot);
     return EA_OK;
 }
 
@@ -445,6 +516,9 @@ static int residual_vectors(ea_handle *h, double out[4]) {
 
 int ea_update_residual(ea_handle_t *h, double out[4]) {
     if (!h || !out) return EA_ERR_ARG;
+    if (h->d.partitioned)
+        return fail(h, EA_ERR_STATE, "step-wise operators act on the local sub-grid only; a partitioned handle is driven "
+                                     "through ea_inner_iteration / ea_run_inner / ea_admm_two_level");
     CK(cudaSetDevice(h->device));
     return residual_vectors(h, out);
 }
@@ -463,8 +537,7 @@ int ea_poststep(ea_handle_t *h, double *objval) {
         const double p = h->d.baseMVA * pg[g];
         obj += h->c2[g] * (p * p) + h->c1[g] * p + h->c0[g];
     }
-    *objval = obj;
-    return EA_OK;
+    return allgather_scalar_sum(h, obj, objval);
 }
 
 // ---- fused path --------------------------------------------------------------------------
@@ -482,9 +555,18 @@ static int enqueue_iteration(ea_handle *h, int max_auglag, double mu_max, double
     int rc = launch_x(h, 0, 0, max_auglag, mu_max, scale, 1, 1);
     if (rc) return rc;
     if (e) CK(cudaEventRecord(e[1], h->stream));
-    k_bus<true><<<nblocks(h->nbus, BBLOCK), BBLOCK, 0, h->stream>>>(h->d, -1, 0.0);
+    k_bus<true><<<nblocks(h->d.nbus_active, BBLOCK), BBLOCK, 0, h->stream>>>(h->d, -1, 0.0);
     CK(cudaGetLastError());
     h->n_bus++;
+    if (h->d.partitioned && !h->loopback) {
+        // the one exchange of the iteration: xbar halves of the cut-branch ends + residual partial sums
+        if (!h->comm) return fail(h, EA_ERR_STATE, "partitioned handle without a communicator (call ea_comm_init)");
+        ncclResult_t r = g_nccl.AllGather(h->d.sendbuf, h->gather_dev, (size_t)h->d.stride, ncclDouble, h->comm, h->stream);
+        if (r != ncclSuccess) return fail(h, EA_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+        k_finish<<<1, FBLOCK, 0, h->stream>>>(h->d);
+        CK(cudaGetLastError());
+        h->n_other++;
+    }
     if (e) CK(cudaEventRecord(e[2], h->stream));
     return EA_OK;
 }
@@ -582,7 +664,7 @@ int ea_admm_two_level(ea_handle_t *h, const ea_params_t *par, ea_info_t *info) {
     double beta = par->initial_beta;
     double res[4];
     int rc;
-    if (par->verbose > 0) {     // admm_two_level.jl:15-25
+    if (par->verbose > 0 && !h->d.partitioned) {     // admm_two_level.jl:15-25
         if ((rc = ea_update_residual(h, res))) return rc;
         info->primres = res[0]; info->dualres = res[1]; info->norm_z_curr = res[2]; info->mismatch = res[3];
         printf("%8s  %8s  %10s  %10s  %10s  %10s  %10s  %10s  %10s  %10s  %10s\n", "Outer", "Inner", "Objval", "AugLag",
@@ -599,15 +681,16 @@ int ea_admm_two_level(ea_handle_t *h, const ea_params_t *par, ea_info_t *info) {
         info->inner = 0;
         if (par->verbose > 0) {
             // per-iteration table: one host round trip per inner iteration
+            const bool talk = !h->d.partitioned || h->part_rank == 0;
             while (info->inner < par->inner_iterlim) {
                 info->inner++; info->cumul++;
                 if ((rc = ea_inner_iteration(h, info->inner, beta, par->max_auglag, par->mu_max, par->scale, res))) return rc;
                 info->primres = res[0]; info->dualres = res[1]; info->norm_z_curr = res[2]; info->mismatch = res[3];
                 info->eps_pri = sqrt_d / (2500.0 * (double)info->outer);
-                if ((info->cumul % 50) == 0)
+                if (talk && (info->cumul % 50) == 0)
                     printf("%8s  %8s  %10s  %10s  %10s  %10s  %10s  %10s  %10s  %10s  %10s\n", "Outer", "Inner", "Objval",
                            "AugLag", "PrimRes", "EpsPrimRes", "DualRes", "||z||", "||Ax+By||", "OuterTol", "Beta");
-                printf("%8lld  %8lld  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e\n",
+                if (talk) printf("%8lld  %8lld  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e  %10.3e\n",
                        (long long)info->outer, (long long)info->inner, info->objval, info->auglag, info->primres,
                        info->eps_pri, info->dualres, info->norm_z_curr, info->mismatch, OUTER_TOL, beta);
                 if (info->primres <= info->eps_pri) break;
@@ -745,6 +828,127 @@ int ea_set_option(ea_handle_t *h, const char *name, double value) {
     return fail(h, EA_ERR_ARG, "ea_set_option: unknown option '%s'", name);
 }
 
+// ---- bus-partitioned multi-GPU mode ------------------------------------------------------------
+int ea_set_partition(ea_handle_t *h, int32_t rank, int32_t nranks, int64_t n_owned_bus, int64_t n_send,
+                     const int64_t *send_line, const int64_t *send_end, int64_t n_ghost, const int64_t *ghost_line,
+                     const int64_t *ghost_end, const int64_t *ghost_src_rank, const int64_t *ghost_src_pos, int64_t max_send) {
+    if (!h) return EA_ERR_ARG;
+    if (nranks < 1 || rank < 0 || rank >= nranks || n_owned_bus < 0 || n_owned_bus > h->nbus || n_send < 0 || n_ghost < 0 ||
+        max_send < n_send || (n_send && (!send_line || !send_end)) ||
+        (n_ghost && (!ghost_line || !ghost_end || !ghost_src_rank || !ghost_src_pos)))
+        return fail(h, EA_ERR_ARG, "ea_set_partition: bad argument");
+    if (h->d.partitioned) return fail(h, EA_ERR_STATE, "ea_set_partition: already partitioned");
+    CK(cudaSetDevice(h->device));
+    // half-slot of (line, end) from the layout built in ea_create
+    std::vector<int> slot_from((size_t)h->nline), slot_to((size_t)h->nline), hstart((size_t)h->nbus + 1);
+    CK(cudaMemcpy(slot_from.data(), h->d.slot_from, sizeof(int) * (size_t)h->nline, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(slot_to.data(), h->d.slot_to, sizeof(int) * (size_t)h->nline, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hstart.data(), h->d.hstart, sizeof(int) * ((size_t)h->nbus + 1), cudaMemcpyDeviceToHost));
+    const int owned_halves = hstart[(size_t)n_owned_bus];
+    const int stride = 4 + 4 * (int)max_send;
+    std::vector<int> send_pos(2 * (size_t)h->nline, -1), ghost_slot((size_t)n_ghost), ghost_src((size_t)n_ghost);
+    for (int64_t k = 0; k < n_send; ++k) {
+        if (send_line[k] < 0 || send_line[k] >= h->nline || (send_end[k] != 0 && send_end[k] != 1))
+            return fail(h, EA_ERR_ARG, "ea_set_partition: bad send entry %lld", (long long)k);
+        const int s = send_end[k] ? slot_to[send_line[k]] : slot_from[send_line[k]];
+        if (s >= owned_halves) return fail(h, EA_ERR_ARG, "ea_set_partition: send entry %lld is not an owned branch end", (long long)k);
+        send_pos[s] = (int)k;
+    }
+    for (int64_t k = 0; k < n_ghost; ++k) {
+        if (ghost_line[k] < 0 || ghost_line[k] >= h->nline || (ghost_end[k] != 0 && ghost_end[k] != 1) ||
+            ghost_src_rank[k] < 0 || ghost_src_rank[k] >= nranks || ghost_src_rank[k] == rank || ghost_src_pos[k] < 0 ||
+            ghost_src_pos[k] >= max_send)
+            return fail(h, EA_ERR_ARG, "ea_set_partition: bad ghost entry %lld", (long long)k);
+        const int s = ghost_end[k] ? slot_to[ghost_line[k]] : slot_from[ghost_line[k]];
+        if (s < owned_halves) return fail(h, EA_ERR_ARG, "ea_set_partition: ghost entry %lld is an owned branch end", (long long)k);
+        ghost_slot[k] = s;
+        ghost_src[k] = (int)(ghost_src_rank[k] * stride + 4 + 4 * ghost_src_pos[k]);
+    }
+    if ((int64_t)owned_halves + n_ghost != 2 * h->nline)
+        return fail(h, EA_ERR_ARG, "ea_set_partition: owned + ghost branch ends do not cover the local grid");
+    int rc;
+    Dev &d = h->d;
+    if ((rc = dev_upload(h, const_cast<int **>(&d.send_pos), send_pos))) return rc;
+    if ((rc = dev_upload(h, const_cast<int **>(&d.ghost_slot), ghost_slot))) return rc;
+    if ((rc = dev_upload(h, const_cast<int **>(&d.ghost_src), ghost_src))) return rc;
+    if ((rc = dev_alloc(h, &h->gather_dev, (size_t)stride * nranks))) return rc;
+    if (cudaMallocHost((void **)&h->gather_host, sizeof(double) * (size_t)stride * nranks) != cudaSuccess)
+        return fail(h, EA_ERR_ALLOC, "cudaMallocHost failed");
+    d.gather = h->gather_dev;
+    d.sendbuf = h->gather_dev + (size_t)rank * stride;
+    d.partitioned = 1; d.rank = rank; d.nranks = nranks; d.n_ghost = (int)n_ghost; d.stride = stride;
+    d.nbus_active = (int)n_owned_bus;
+    h->part_rank = rank; h->part_nranks = nranks;
+    h->n_owned_entries = (int64_t)h->gpad + 4 * (int64_t)owned_halves;
+    return EA_OK;
+}
+
+int ea_nccl_unique_id(const char *nccl_lib, char out[128]) {
+    ea_handle *h = nullptr;
+    if (!out) return EA_ERR_ARG;
+    if (const char *e = load_nccl(nccl_lib)) return fail(h, EA_ERR_NCCL, "%s", e);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(h, EA_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    memcpy(out, &id, 128);
+    return EA_OK;
+}
+
+int ea_comm_init(ea_handle_t *h, const char *nccl_lib, const char id[128]) {
+    if (!h || !id) return EA_ERR_ARG;
+    if (!h->d.partitioned) return fail(h, EA_ERR_STATE, "ea_comm_init: call ea_set_partition first");
+    if (const char *e = load_nccl(nccl_lib)) return fail(h, EA_ERR_NCCL, "%s", e);
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, h->part_nranks, uid, h->part_rank);
+    if (r != ncclSuccess) return fail(h, EA_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    return EA_OK;
+}
+
+// Loopback exchange for single-GPU tests: the caller moves the message through the host.
+// ea_part_begin = x-update + bus kernel; ea_part_get_message -> this rank's segment;
+// ea_part_put_gathered <- all segments; ea_part_end = k_finish, returns the 4 norms.
+int ea_part_begin(ea_handle_t *h, int64_t inner, double beta, int32_t max_auglag, double mu_max, double scale) {
+    if (!h) return EA_ERR_ARG;
+    if (!h->d.partitioned) return fail(h, EA_ERR_STATE, "ea_part_begin: not a partitioned handle");
+    CK(cudaSetDevice(h->device));
+    int rc = sync_ctrl_to_device(h, beta, -1.0, inner - 1, std::numeric_limits<long long>::max());
+    if (rc) return rc;
+    h->loopback = 1;
+    rc = enqueue_iteration(h, max_auglag, mu_max, scale, 0);
+    h->loopback = 0;
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return EA_OK;
+}
+int ea_part_get_message(ea_handle_t *h, double *host, int64_t n) {
+    if (!h || !host) return EA_ERR_ARG;
+    if (!h->d.partitioned || n != h->d.stride) return fail(h, EA_ERR_ARG, "ea_part_get_message: n must be the stride %d", h->d.stride);
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(host, h->d.sendbuf, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    return EA_OK;
+}
+int ea_part_put_gathered(ea_handle_t *h, const double *host, int64_t n) {
+    if (!h || !host) return EA_ERR_ARG;
+    if (!h->d.partitioned || n != (int64_t)h->d.stride * h->part_nranks) return fail(h, EA_ERR_ARG, "ea_part_put_gathered: bad n");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(h->gather_dev, host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    return EA_OK;
+}
+int ea_part_end(ea_handle_t *h, double out[4]) {
+    if (!h || !out) return EA_ERR_ARG;
+    if (!h->d.partitioned) return fail(h, EA_ERR_STATE, "ea_part_end: not a partitioned handle");
+    CK(cudaSetDevice(h->device));
+    k_finish<<<1, FBLOCK, 0, h->stream>>>(h->d);
+    CK(cudaGetLastError());
+    int rc = fetch_ctrl(h);
+    if (rc) return rc;
+    for (int k = 0; k < 4; ++k) out[k] = h->ctrl_host->res[k];
+    return EA_OK;
+}
+
 int ea_diag_branch_eval(int device, int64_t n, const double *x, const double *param, const double *Y, double scale,
                         double *f, double *g, double *H) {
     ea_handle *h = nullptr;
@@ -763,6 +967,35 @@ int ea_diag_branch_eval(int device, int64_t n, const double *x, const double *pa
     CK(cudaMemcpy(g, dg, 6 * n * sizeof(double), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(H, dH, 36 * n * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dp); cudaFree(dY); cudaFree(df); cudaFree(dg); cudaFree(dH);
+    return EA_OK;
+}
+
+int ea_diag_fp64_peak(int device, double *tflops) {
+    ea_handle *h = nullptr;
+    if (!tflops) return EA_ERR_ARG;
+    if (ea_device_count() <= 0) return fail(h, EA_ERR_CUDA, "ea_diag_fp64_peak: no CUDA device");
+    CK(cudaSetDevice(device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double *out;
+    CK(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_fp64_peak<<<blocks, threads>>>(out, 64);           // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(out, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 64.0 * iters * (double)blocks * threads;     // 64 FMAs per loop trip
+        best = std::max(best, fl / (1e-3 * ms) / 1e12);
+    }
+    CK(cudaGetLastError());
+    cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
     return EA_OK;
 }
 

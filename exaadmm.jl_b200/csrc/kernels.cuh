@@ -55,6 +55,14 @@ struct Dev {                  // everything the kernels need, passed by value
     Ctrl *ctrl;
     Counters *counters;
     int count_work;
+    // bus-partitioned multi-GPU mode (0 / null when the handle holds the whole grid)
+    int nbus_active;                      // buses this rank updates (owned buses come first); == nbus otherwise
+    int partitioned, rank, nranks, n_ghost, stride;
+    const int *send_pos;                  // per half-slot: position in this rank's send list, or -1
+    double *sendbuf;                      // this rank's segment of `gather`: [4 partial sums | 4 doubles per send entry]
+    const double *gather;                 // nranks x stride, filled by the all-gather
+    const int *ghost_slot;                // half-slot of every ghost end
+    const int *ghost_src;                 // index of its xbar record in `gather`
 };
 
 // ---------------------------------------------------------------------------
@@ -374,7 +382,7 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
     double *znew = d.zbuf[zsel ^ 1];
     const int b = blockIdx.x * BBLOCK + threadIdx.x;
     double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
-    if (b < d.nbus) {
+    if (b < d.nbus_active) {
         const int hs = d.hstart[b], he = d.hstart[b + 1], gs = d.gstart[b], ge = d.gstart[b + 1];
         const double *uh = d.u + d.gpad, *zh = zold + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
         double common_wi = 0.0, common_ti = 0.0, inv_p = 0.0, inv_q = 0.0, rs_w = 0.0, rs_t = 0.0;
@@ -450,6 +458,10 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
             v.w = wi;
             v.t = ti;
             st4(d.v + d.gpad, s, v);
+            if (d.send_pos) {                      // cut-branch end: its xbar also goes into the exchange message
+                const int sp = d.send_pos[s];
+                if (sp >= 0) st4(d.sendbuf + 4, sp, v);
+            }
             if (FUSED) {
                 const d4 lz = ld4(d.lz + d.gpad, s);
                 d4 zn, ln;
@@ -476,7 +488,12 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
         }
     }
     if (FUSED) {
-        if (grid_sum4<BBLOCK>(acc, d.partials, &d.ctrl->ticket, red) && threadIdx.x == 0) {
+        const bool last = grid_sum4<BBLOCK>(acc, d.partials, &d.ctrl->ticket, red);
+        if (last && threadIdx.x == 0 && d.partitioned) {
+            // partial sums over this rank's entries; norms and the termination test follow the all-gather (k_finish)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d.sendbuf[k] = acc[k];
+        } else if (last && threadIdx.x == 0) {
             Ctrl *c = d.ctrl;
 #pragma unroll
             for (int k = 0; k < 4; ++k) c->res[k] = sqrt(acc[k]);
@@ -488,6 +505,48 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
             if (c->res[0] <= c->eps_pri || inner >= c->inner_limit) c->done = 1;
         }
     }
+}
+
+// Partitioned mode, after the all-gather: install the received xbar halves of the ghost
+// ends, update their z and lambda redundantly (same formulas, same inputs as on the
+// owner), then add the ranks' partial sums in rank order and run the termination test.
+constexpr int FBLOCK = 256;
+__global__ void __launch_bounds__(FBLOCK) k_finish(Dev d) {
+    Ctrl *c = d.ctrl;
+    if (c->done) return;
+    const int zsel = c->zsel;
+    const double beta = c->beta;
+    const double *zold = d.zbuf[zsel];
+    double *znew = d.zbuf[zsel ^ 1];
+    for (int g = threadIdx.x; g < d.n_ghost; g += FBLOCK) {
+        const int s = d.ghost_slot[g];
+        const double *src = d.gather + d.ghost_src[g];
+        d4 v; v.p = src[0]; v.q = src[1]; v.w = src[2]; v.t = src[3];
+        st4(d.v + d.gpad, s, v);
+        const d4 u = ld4(d.u + d.gpad, s), l = ld4(d.l + d.gpad, s), r = ld4(d.rho + d.gpad, s), lz = ld4(d.lz + d.gpad, s);
+        d4 zn, ln;
+        zn.p = z_update(lz.p, l.p, r.p, u.p, v.p, beta); zn.q = z_update(lz.q, l.q, r.q, u.q, v.q, beta);
+        zn.w = z_update(lz.w, l.w, r.w, u.w, v.w, beta); zn.t = z_update(lz.t, l.t, r.t, u.t, v.t, beta);
+        ln.p = l_update(lz.p, beta, zn.p); ln.q = l_update(lz.q, beta, zn.q);
+        ln.w = l_update(lz.w, beta, zn.w); ln.t = l_update(lz.t, beta, zn.t);
+        st4(znew + d.gpad, s, zn);
+        st4(d.l + d.gpad, s, ln);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot[4] = { 0.0, 0.0, 0.0, 0.0 };
+        for (int r = 0; r < d.nranks; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tot[k] += d.gather[(size_t)r * d.stride + k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c->res[k] = sqrt(tot[k]);
+        const long long inner = c->inner + 1;
+        c->inner = inner;
+        c->zsel = zsel ^ 1;
+        c->next_line = 0;
+        if (c->res[0] <= c->eps_pri || inner >= c->inner_limit) c->done = 1;
+    }
+    (void)zold;
 }
 
 // ---------------------------------------------------------------------------
@@ -588,6 +647,22 @@ __global__ void k_diag_eval(int n, const double *x, const double *param, const d
 #pragma unroll
         for (int b = 0; b < 6; ++b) H[36 * (size_t)i + 6 * a + b] = A.a[tron::tri(a, b)];
     }
+}
+
+// FP64 FMA peak probe: 8 independent DFMA chains per thread (roofline denominator of the
+// branch kernel; MEASURED_PEAKS.json only has HBM and bf16 numbers).
+__global__ void k_fp64_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 }  // namespace ea

@@ -219,6 +219,36 @@ int  ea_set_load(ea_handle_t *h, const double *Pd, const double *Qd, int64_t nbu
 int  ea_set_pg_bounds(ea_handle_t *h, const double *pgmin_curr,
                       const double *pgmax_curr, int64_t ngen);
 
+/* ---- bus-partitioned multi-GPU mode (one process per GPU; new design, the reference is
+ * single-GPU: SURVEY.md F6 / section 8e) -----------------------------------------------------
+ * The handle is created on the RANK-LOCAL grid (owned buses first, then the ghost buses at
+ * the far end of cut branches; exaadmm.jl_b200/partition.py builds it). ea_set_partition
+ * declares which branch ends are sent / received; indices here are 0-BASED local ids,
+ * end = 0 (from) or 1 (to). Every rank's send list has at most max_send entries; a ghost end
+ * takes its xbar from position ghost_src_pos of rank ghost_src_rank's list. Afterwards the
+ * fused entry points (ea_inner_iteration, ea_run_inner*, ea_admm_two_level) run the
+ * partitioned iteration: x-update (cut branches redundantly on both ranks), bus update of the
+ * owned buses, ONE ncclAllGather per inner iteration carrying the xbar halves of the cut
+ * branch ends and each rank's 4 residual partial sums, then the ghost z / lambda update and
+ * the termination test (identical on every rank). */
+int  ea_set_partition(ea_handle_t *h, int32_t rank, int32_t nranks, int64_t n_owned_bus,
+                      int64_t n_send, const int64_t *send_line, const int64_t *send_end,
+                      int64_t n_ghost, const int64_t *ghost_line, const int64_t *ghost_end,
+                      const int64_t *ghost_src_rank, const int64_t *ghost_src_pos, int64_t max_send);
+/* NCCL is dlopen'ed (nccl_lib = path, or NULL: $EXAADMM_NCCL_LIB, then libnccl.so.2). Rank 0
+ * makes the id, the caller broadcasts the 128 bytes (e.g. torch.distributed), every rank
+ * calls ea_comm_init. */
+int  ea_nccl_unique_id(const char *nccl_lib, char out[128]);
+int  ea_comm_init(ea_handle_t *h, const char *nccl_lib, const char id[128]);
+/* Loopback form of one partitioned iteration for single-GPU tests (the caller carries the
+ * message through the host): begin = x-update + bus kernel; get_message = this rank's
+ * segment (stride = 4 + 4*max_send doubles); put_gathered = all nranks segments;
+ * end = ghost update + norms + termination bookkeeping, out = the 4 norms. */
+int  ea_part_begin(ea_handle_t *h, int64_t inner, double beta, int32_t max_auglag, double mu_max, double scale);
+int  ea_part_get_message(ea_handle_t *h, double *host, int64_t n);
+int  ea_part_put_gathered(ea_handle_t *h, const double *host, int64_t n);
+int  ea_part_end(ea_handle_t *h, double out[4]);
+
 int  ea_get_counters(ea_handle_t *h, ea_counters_t *out);
 int  ea_reset_counters(ea_handle_t *h);
 /* Options: "count_work" (0/1, atomics for ea_counters_t in the branch kernel, default 1),
@@ -234,6 +264,10 @@ int  ea_get_kernel_times(ea_handle_t *h, double out[8]);
  * n points on the device; param = 31 doubles per point (one membuf column), Y = 8. */
 int  ea_diag_branch_eval(int device, int64_t n, const double *x, const double *param,
                          const double *Y, double scale, double *f, double *g, double *H);
+
+/* Diagnostics: measured FP64 FMA throughput of the device in TFLOP/s (8 independent
+ * DFMA chains per thread, best of 5); the roofline denominator of the branch kernel. */
+int  ea_diag_fp64_peak(int device, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -254,3 +254,48 @@ def test_set_load_changes_only_the_bus_update(case9_grid):
         ops.admm_inner_iteration(env, mod); ops.admm_increment_inner(env, mod)
     np.testing.assert_allclose(mod.solution.v_curr, om.vec("v_curr"), atol=ITERATE_TOL, rtol=0)
     mod.close()
+
+
+# ---- bus-partitioned mode on ONE GPU (loopback exchange through the host) ------------------
+@pytest.mark.parametrize("nparts", [2, 3])
+def test_partitioned_iteration_matches_single_domain_bitwise(nparts):
+    from exaadmm_b200.partition import assemble_global, partition_buses
+    from exaadmm_b200.partitioned import loopback_iteration, make_partitioned_model
+    d = synthetic_case(400, 60, 560, seed=400)
+    env = AdmmEnv(d, 4e2, 4e4, use_gpu=True, verbose=0, tight_factor=0.99)
+    ref = ModelAcopf(env)
+    grid = ref.grid_data
+    part = partition_buses(grid, nparts)
+    mods, lgs = [], []
+    for r in range(nparts):
+        m, lg = make_partitioned_model(env, grid, part, r)
+        mods.append(m); lgs.append(lg)
+    ops.admm_increment_outer(env, ref); ops.admm_outer_prestep(env, ref); ops.admm_increment_reset_inner(env, ref)
+    beta = env.params.beta
+    for it in range(1, 16):
+        ops.admm_increment_inner(env, ref); ops.admm_inner_iteration(env, ref)
+        res = loopback_iteration(mods, it, beta)
+        want = np.array([ref.info.primres, ref.info.dualres, ref.info.norm_z_curr, ref.info.mismatch])
+        np.testing.assert_allclose(res, want, rtol=1e-12)                  # summation order differs
+    for name in ("u_curr", "v_curr", "z_curr", "z_prev", "l_curr"):
+        glob = assemble_global(lgs, [getattr(m.solution, name) for m in mods], ref.nvar)
+        np.testing.assert_array_equal(glob, getattr(ref.solution, name))  # same kernels, same order: bitwise
+    # ghost copies equal the owner's values
+    gv = ref.solution.v_curr
+    for m, lg in zip(mods, lgs):
+        np.testing.assert_array_equal(m.solution.v_curr, gv[lg.entry_global])
+        m.close()
+    ref.close()
+
+
+def test_step_wise_operators_refuse_a_partitioned_handle():
+    from exaadmm_b200.partition import partition_buses
+    from exaadmm_b200.partitioned import make_partitioned_model
+    from exaadmm_b200.capi import EaError
+    d = synthetic_case(200, 30, 280, seed=200)
+    env = AdmmEnv(d, 4e2, 4e4, use_gpu=True, verbose=0)
+    grid = ea.GridData.from_opfdata(d)
+    m, _ = make_partitioned_model(env, grid, partition_buses(grid, 2), 0)
+    with pytest.raises(EaError, match="partitioned"):
+        ops.admm_update_residual(env, m)
+    m.close()
