@@ -140,7 +140,7 @@ SIGNATURES = {
     "ea_set_load": (C.c_int, [_H, _pd, _pd, C.c_int64]),
     "ea_set_pg_bounds": (C.c_int, [_H, _pd, _pd, C.c_int64]),
     "ea_set_partition": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _pi, _pi, C.c_int64, _pi, _pi, _pi, _pi,
-                                   C.c_int64]),
+                                   C.c_int64, C.c_int64]),
     "ea_nccl_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "ea_comm_init": (C.c_int, [_H, C.c_char_p, C.c_char_p]),
     "ea_part_begin": (C.c_int, [_H, C.c_int64, C.c_double, C.c_int32, C.c_double, C.c_double]),

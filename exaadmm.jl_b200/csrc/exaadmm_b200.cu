@@ -61,6 +61,7 @@ struct ea_handle {
     // bus-partitioned multi-GPU mode
     int part_rank = 0, part_nranks = 1;
     int64_t n_owned_entries = 0;                // prefix of the HBM layout owned by this rank
+    int64_t nvar_global = 0;                    // size of the whole problem (tolerances scale with sqrt of it)
     double *gather_dev = nullptr;               // nranks x stride
     double *gather_host = nullptr;              // pinned mirror (scalar collectives, loopback tests)
     ncclComm_t comm = nullptr;
@@ -343,6 +344,7 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     d.count_work = 1;
     d.nbus_active = nbus;
     h->n_owned_entries = nint;
+    h->nvar_global = h->nvar;
     if (cudaMallocHost((void **)&h->ctrl_host, sizeof(Ctrl)) != cudaSuccess) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
     if (cudaMallocHost((void **)&h->res_host, 4 * sizeof(double)) != cudaSuccess) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
     memset(h->ctrl_host, 0, sizeof(Ctrl));
@@ -600,7 +602,7 @@ int ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_
     if (outer < 1 || inner_start < 0 || inner_limit < inner_start) return fail(h, EA_ERR_ARG, "ea_run_inner: bad outer / inner range");
     CK(cudaSetDevice(h->device));
     if (chunk <= 0) chunk = h->default_chunk;
-    const double eps_pri = std::sqrt((double)h->nvar) / (2500.0 * (double)outer);    // admm_two_level.jl:45
+    const double eps_pri = std::sqrt((double)h->nvar_global) / (2500.0 * (double)outer);    // admm_two_level.jl:45
     if (inner_limit == inner_start) { *inner_done = inner_start; for (int k = 0; k < 4; ++k) out[k] = 0.0; return EA_OK; }
     CK(cudaEventRecord(h->span0, h->stream));
     int rc = sync_ctrl_to_device(h, beta, eps_pri, inner_start, inner_limit);
@@ -657,7 +659,7 @@ int ea_get_kernel_times(ea_handle_t *h, double out[8]) {
 int ea_admm_two_level(ea_handle_t *h, const ea_params_t *par, ea_info_t *info) {
     if (!h || !par || !info) return EA_ERR_ARG;
     CK(cudaSetDevice(h->device));
-    const double sqrt_d = std::sqrt((double)h->nvar);
+    const double sqrt_d = std::sqrt((double)h->nvar_global);
     const double OUTER_TOL = sqrt_d * par->outer_eps;
     memset(info, 0, sizeof(*info));
     info->mismatch = INFINITY; info->norm_z_prev = INFINITY; info->norm_z_curr = INFINITY;
@@ -831,10 +833,11 @@ int ea_set_option(ea_handle_t *h, const char *name, double value) {
 // ---- bus-partitioned multi-GPU mode ------------------------------------------------------------
 int ea_set_partition(ea_handle_t *h, int32_t rank, int32_t nranks, int64_t n_owned_bus, int64_t n_send,
                      const int64_t *send_line, const int64_t *send_end, int64_t n_ghost, const int64_t *ghost_line,
-                     const int64_t *ghost_end, const int64_t *ghost_src_rank, const int64_t *ghost_src_pos, int64_t max_send) {
+                     const int64_t *ghost_end, const int64_t *ghost_src_rank, const int64_t *ghost_src_pos, int64_t max_send,
+                     int64_t nvar_global) {
     if (!h) return EA_ERR_ARG;
     if (nranks < 1 || rank < 0 || rank >= nranks || n_owned_bus < 0 || n_owned_bus > h->nbus || n_send < 0 || n_ghost < 0 ||
-        max_send < n_send || (n_send && (!send_line || !send_end)) ||
+        max_send < n_send || nvar_global < h->nvar - 8 * n_ghost / 2 || (n_send && (!send_line || !send_end)) ||
         (n_ghost && (!ghost_line || !ghost_end || !ghost_src_rank || !ghost_src_pos)))
         return fail(h, EA_ERR_ARG, "ea_set_partition: bad argument");
     if (h->d.partitioned) return fail(h, EA_ERR_STATE, "ea_set_partition: already partitioned");
@@ -880,6 +883,7 @@ int ea_set_partition(ea_handle_t *h, int32_t rank, int32_t nranks, int64_t n_own
     d.nbus_active = (int)n_owned_bus;
     h->part_rank = rank; h->part_nranks = nranks;
     h->n_owned_entries = (int64_t)h->gpad + 4 * (int64_t)owned_halves;
+    h->nvar_global = nvar_global;
     return EA_OK;
 }
 

@@ -46,7 +46,7 @@ def make_partitioned_model(env: AdmmEnv, grid: GridData, part: np.ndarray, rank:
             (lg.send_line, lg.send_end, lg.ghost_line, lg.ghost_end, lg.ghost_src_rank, lg.ghost_src_pos)]
     mod._check(mod.lib.ea_set_partition(mod.h, rank, lg.nparts, lg.n_owned_bus, len(lg.send_line), _ip(keep[0]), _ip(keep[1]),
                                         len(lg.ghost_line), _ip(keep[2]), _ip(keep[3]), _ip(keep[4]), _ip(keep[5]),
-                                        lg.max_send))
+                                        lg.max_send, 2 * grid.ngen + 8 * grid.nline))
     mod.local_grid = lg
     return mod, lg
 

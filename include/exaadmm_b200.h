@@ -234,7 +234,8 @@ int  ea_set_pg_bounds(ea_handle_t *h, const double *pgmin_curr,
 int  ea_set_partition(ea_handle_t *h, int32_t rank, int32_t nranks, int64_t n_owned_bus,
                       int64_t n_send, const int64_t *send_line, const int64_t *send_end,
                       int64_t n_ghost, const int64_t *ghost_line, const int64_t *ghost_end,
-                      const int64_t *ghost_src_rank, const int64_t *ghost_src_pos, int64_t max_send);
+                      const int64_t *ghost_src_rank, const int64_t *ghost_src_pos, int64_t max_send,
+                      int64_t nvar_global /* 2*ngen + 8*nline of the WHOLE case: eps_pri and OUTER_TOL scale with its sqrt */);
 /* NCCL is dlopen'ed (nccl_lib = path, or NULL: $EXAADMM_NCCL_LIB, then libnccl.so.2). Rank 0
  * makes the id, the caller broadcasts the 128 bytes (e.g. torch.distributed), every rank
  * calls ea_comm_init. */

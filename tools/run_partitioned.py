@@ -24,6 +24,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 _, data = bench.make_grid(wl)
 par, rho_pq, rho_va = bench.default_params(wl)
+if len(sys.argv) > 3:                      # optional rho override: workload rho_pq rho_va
+    rho_pq, rho_va = float(sys.argv[2]), float(sys.argv[3])
 kw = dict(rho_pq=rho_pq, rho_va=rho_va, scale=par.scale, tight_factor=0.99, outer_iterlim=20, inner_iterlim=1000)
 grid = ea.GridData.from_opfdata(data, tight_factor=0.99)
 part = partition_buses(grid, world)
