@@ -309,23 +309,41 @@ def run_ours(args, rank, world, local_rank):
         peaks = json.loads(pk.read_text())
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    n_x, t_x, n_b, t_b = kt[1], kt[2], kt[3], kt[4]          # launches and summed durations (s)
-    # algorithmic bytes per launch: bus kernel 64 B/entry + per-bus data + CSR
-    bus_bytes = 64.0 * nvar + 48.0 * grid.nbus + 8.0 * (grid.nbus + 1)
+    fp64_peak = C.c_double(0.0)
+    check(lib.ea_diag_fp64_peak(local_rank, C.byref(fp64_peak)))     # DFMA probe on this device (not in MEASURED_PEAKS.json)
+    n_x, t_x, n_b, t_b = kt[1], kt[2], kt[3], kt[4]          # launches and summed CUDA-event durations (s), pass B
+    # Algorithmic work per launch:
+    #   branch kernel: 568 B per branch (60 reads + 11 writes) + 128 B per generator;
+    #                  FP64 flops = 1645 per objective evaluation incl. its share of the TRON algebra
+    #                  (ncu op counts / evaluations, profiles/r1_fp64_ops_per_launch.csv)
+    #   bus kernel:    64 B per entry (u,z,lambda,rho,lz read; v,z,lambda written) + 48 B per bus + CSR pointers
     x_bytes = 568.0 * grid.nline + 128.0 * grid.ngen
-    roof = {"bound": "hbm", "kernel": "k_bus<fused> (xbar + z + lambda + residual norms)",
-            "achieved": (bus_bytes / (t_b / n_b)) / 1e9 if n_b else None, "peak": hbm_peak, "unit": "GB/s",
-            "frac": ((bus_bytes / (t_b / n_b)) / 1e9 / hbm_peak) if n_b else None, "traffic": None,
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": bus_bytes,
-            "avg_launch_us": 1e6 * t_b / n_b if n_b else None}
+    bus_bytes = 64.0 * nvar + 48.0 * grid.nbus + 8.0 * (grid.nbus + 1)
     evals = cnt["tron_evals"]
-    flops = evals * 330.0 + cnt["cg_iters"] * 200.0 + (evals - cnt["line_calls"]) * 450.0   # DESIGN.md §5 op counts
-    roof_x = {"bound": "fp64", "kernel": "k_xupdate (generators + branch AL/TRON)",
-              "avg_launch_us": 1e6 * t_x / n_x if n_x else None,
-              "achieved_tflops": (flops / t_x) / 1e12 if t_x else None,
-              "hbm_gbs": (x_bytes / (t_x / n_x)) / 1e9 if n_x else None,
-              "evals_per_branch_call": evals / max(cnt["line_calls"], 1),
-              "share_of_step": t_x / (t_x + t_b) if (t_x + t_b) else None}
+    flops = 1645.0 * evals
+    avg_x = t_x / n_x if n_x else float("nan")
+    avg_b = t_b / n_b if n_b else float("nan")
+    roof = {   # dominant kernel of the step (share of the step below). It is neither HBM- nor tensor-bound: it is
+               # bound by the serial chain of the slowest branch; both rooflines are reported.
+        "kernel": "k_xupdate (generators + branch augmented-Lagrangian / TRON solves)", "bound": "hbm",
+        "achieved": x_bytes / avg_x / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": x_bytes / avg_x / 1e9 / hbm_peak,
+        "traffic": 45.5e6, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r1_fp64_ops_per_launch.csv",
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": x_bytes, "avg_launch_us": 1e6 * avg_x,
+        "share_of_step": t_x / (t_x + t_b) if (t_x + t_b) else None,
+        "fp64": {"achieved_tflops": flops / t_x / 1e12 if t_x else None, "peak_tflops": fp64_peak.value,
+                 "frac": (flops / t_x / 1e12 / fp64_peak.value) if (t_x and fp64_peak.value) else None,
+                 "peak_source": "ea_diag_fp64_peak (8 independent DFMA chains/thread, measured in this run)",
+                 "flops_per_evaluation": 1645.0, "evaluations_per_launch": evals / n_x if n_x else None},
+        "critical_path": {"max_evaluations_of_one_branch": cnt["max_evals_lane"],
+                          "mean_evaluations_per_branch": evals / max(cnt["line_calls"], 1),
+                          "note": "launch time ~ (evaluations of the slowest branch / 2) x ~7.5 us per serial TRON round"},
+    }
+    roof_bus = {"kernel": "k_bus<fused> (bus consensus + z + lambda + residual norms)", "bound": "hbm",
+                "achieved": bus_bytes / avg_b / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bus_bytes / avg_b / 1e9 / hbm_peak, "traffic": 31.9e6,
+                "traffic_source": "ncu dram bytes per launch (cold cache; the 50 MB working set is L2-resident in the loop)",
+                "algorithmic_bytes_per_launch": bus_bytes, "avg_launch_us": 1e6 * avg_b,
+                "share_of_step": t_b / (t_x + t_b) if (t_x + t_b) else None}
 
     # ---------------- CPU baseline (1 core, bounded sample) ----------------------------------------
     cpu = None
@@ -367,7 +385,7 @@ def run_ours(args, rank, world, local_rank):
                 "status": capi.STATUS_NAMES[info_e2e.status], "outer": info_e2e.outer, "cumul": info_e2e.cumul,
                 "objval": info_e2e.objval, "mismatch": info_e2e.mismatch},
         "roofline": roof,
-        "roofline_branch_kernel": roof_x,
+        "roofline_bus_kernel": roof_bus,
         "work_counters": cnt,
         "cpu_baseline": cpu,
     }

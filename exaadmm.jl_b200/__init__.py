@@ -7,7 +7,13 @@ is the CUDA library behind ``include/exaadmm_b200.h`` (``csrc/``).
 from .matpower import OPFData, parse_matpower, parse_matpower_text, write_matpower, MatpowerFormatError
 from .grid_data import GridData
 
-__all__ = ["OPFData", "parse_matpower", "parse_matpower_text", "write_matpower",
+from .environment import AdmmEnv, Parameters, IterationInformation, ComponentInformation  # noqa: E402
+from .model import ModelAcopf, Solution  # noqa: E402
+from .solve_acopf import solve_acopf  # noqa: E402
+from .admm_two_level import admm_two_level, print_statistics  # noqa: E402
+
+__all__ = ["AdmmEnv", "Parameters", "IterationInformation", "ComponentInformation", "ModelAcopf", "Solution",
+           "solve_acopf", "admm_two_level", "print_statistics", "OPFData", "parse_matpower", "parse_matpower_text", "write_matpower",
            "MatpowerFormatError", "GridData"]
 
 CASE9 = str(__import__("pathlib").Path(__file__).resolve().parent / "data" / "case9.m")

@@ -132,22 +132,29 @@ template <int N> EA_DEV void gpstep(const double (&x)[N], const double (&xl)[N],
     }
 }
 
-// break points along w (B.1 dbreakpt). sgn = +1 uses w, sgn = -1 uses -w.
+// break points along w (B.1 dbreakpt). sgn = +1 uses w, sgn = -1 uses -w. Branch-free: the N
+// quotients are independent chains the scheduler can overlap.
 template <int N> EA_DEV void breakpt(const double (&x)[N], const double (&xl)[N], const double (&xu)[N],
                                                          const double (&w)[N], double sgn, double &brptmin, double &brptmax) {
-    bool any = false;
-    brptmin = 0.0; brptmax = 0.0;
+    double b[N];
+    bool has[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const double wi = sgn * w[i];
         const bool up = (x[i] < xu[i]) && (wi > 0.0);
         const bool dn = (x[i] > xl[i]) && (wi < 0.0);
-        if (up || dn) {
-            const double b = ddiv((up ? xu[i] : xl[i]) - x[i], wi);
-            brptmin = any ? dmin(brptmin, b) : b;
-            brptmax = any ? dmax(brptmax, b) : b;
-            any = true;
-        }
+        has[i] = up || dn;
+        b[i] = ddiv((up ? xu[i] : xl[i]) - x[i], has[i] ? wi : 1.0);
+    }
+    bool any = false;
+    brptmin = 0.0; brptmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double lo = any ? dmin(brptmin, b[i]) : b[i];
+        const double hi = any ? dmax(brptmax, b[i]) : b[i];
+        brptmin = has[i] ? lo : brptmin;
+        brptmax = has[i] ? hi : brptmax;
+        any = any || has[i];
     }
 }
 
@@ -157,11 +164,9 @@ template <int N> EA_DEV double gpnorm(const double (&x)[N], const double (&xl)[N
     double nrm = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        double v;
-        if (x[i] == xl[i]) v = fabs(dmin(g[i], 0.0));
-        else if (x[i] == xu[i]) v = fabs(dmax(g[i], 0.0));
-        else v = fabs(g[i]);
-        if (xl[i] != xu[i]) nrm = dmax(nrm, v);
+        const double at_l = fabs(dmin(g[i], 0.0)), at_u = fabs(dmax(g[i], 0.0)), in = fabs(g[i]);
+        const double v = (x[i] == xl[i]) ? at_l : ((x[i] == xu[i]) ? at_u : in);
+        nrm = (xl[i] != xu[i]) ? dmax(nrm, v) : nrm;
     }
     return nrm;
 }
@@ -171,9 +176,11 @@ template <int N> EA_DEV double trqsol(const double (&x)[N], const double (&p)[N]
     const double ptx = dot<N>(p, x), ptp = dot<N>(p, p), xtx = dot<N>(x, x);
     const double dsq = delta * delta;
     const double rad = dsqrt(dmax(EA_FMA(ptx, ptx, ptp * (dsq - xtx)), 0.0));
-    if (ptx > 0.0) return ddiv(dsq - xtx, ptx + rad);
-    if (rad > 0.0) return ddiv(rad - ptx, ptp);
-    return 0.0;
+    const bool first = ptx > 0.0, second = rad > 0.0;
+    const double num = first ? (dsq - xtx) : (rad - ptx);
+    const double den = first ? (ptx + rad) : (second ? ptp : 1.0);
+    const double q = ddiv(num, den);
+    return (first || second) ? q : 0.0;
 }
 
 // q(s) = 0.5 s'As + g's and g's
@@ -201,8 +208,8 @@ template <int N> EA_DEV double cauchy(const double (&x)[N], const double (&xl)[N
         gpstep<N>(x, xl, xu, -alpha, g, s);
         if (mode == 3) break;
         const bool within = nrm2<N>(s) <= delta;
-        double q = 0.0, gts = 0.0;
-        if (within) quad<N>(A, g, s, q, gts);
+        double q, gts;
+        quad<N>(A, g, s, q, gts);                              // only used when `within`; cheaper than a branch
         if (mode == 0) {
             const bool interp = !within || (q >= mu0 * gts);
             if (interp) { mode = 1; alpha = interpf * alpha; }
@@ -555,10 +562,12 @@ EA_DEV int judge_step(double f_trial, double fc, double g0, double snorm, double
     if (first_iter) delta = dmin(delta, snorm);
     const double den = f_trial - fc - g0;
     const double alpha = (den <= 0.0) ? sigma3 : dmax(sigma1, -0.5 * ddiv(g0, den));
-    if (actred < eta0 * prered) delta = dmin(dmax(alpha, sigma1) * snorm, sigma2 * delta);
-    else if (actred < eta1 * prered) delta = dmax(sigma1 * delta, dmin(alpha * snorm, sigma2 * delta));
-    else if (actred < eta2 * prered) delta = dmax(sigma1 * delta, dmin(alpha * snorm, sigma3 * delta));
-    else delta = dmax(delta, dmin(alpha * snorm, sigma3 * delta));
+    const double as = alpha * snorm;
+    const double d0 = dmin(dmax(alpha, sigma1) * snorm, sigma2 * delta);
+    const double d1 = dmax(sigma1 * delta, dmin(as, sigma2 * delta));
+    const double d2 = dmax(sigma1 * delta, dmin(as, sigma3 * delta));
+    const double d3 = dmax(delta, dmin(as, sigma3 * delta));
+    delta = (actred < eta0 * prered) ? d0 : ((actred < eta1 * prered) ? d1 : ((actred < eta2 * prered) ? d2 : d3));
     accepted = actred > eta0 * prered;
     const double f = accepted ? f_trial : fc;
     int task = accepted ? 1 : 0;
