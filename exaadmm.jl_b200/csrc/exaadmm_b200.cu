@@ -54,6 +54,7 @@ struct ea_handle {
     double span_s = 0.0;                        // device time spent inside ea_run_inner* calls (events on h->stream)
     long long n_x = 0, n_bus = 0, n_other = 0;  // kernels launched
     double t_x = 0.0, t_bus = 0.0;              // summed durations (kernel_timing only)
+    long long n_timed = 0;                      // iterations those sums cover (no-op launches after `done` excluded)
     int kernel_timing = 0;
     int loopback = 0;                           // tests: exchange done by the caller through the host
     std::vector<cudaEvent_t> kev;               // event pool for kernel_timing
@@ -179,6 +180,29 @@ int launch_x(ea_handle *h, long long major, int zsel, int max_auglag, double mu_
     return EA_OK;
 }
 
+// Pack consecutive buses into warps of the bus kernel: the ends of a warp's buses fill at most 32 lanes; a bus
+// with more than 32 ends (or none) gets a warp of its own and takes the scalar path. The result is one int4 per
+// (warp, lane): {end slot or -1, bus, lane - leader lane, #ends of the bus if this lane leads it}.
+int build_bus_warps(ea_handle *h, const std::vector<int> &hstart, int nbus_active) {
+    std::vector<int4> info;
+    auto flush = [&](std::vector<int4> &w) { w.resize(32, make_int4(-1, 0, 0, 0)); info.insert(info.end(), w.begin(), w.end()); w.clear(); };
+    std::vector<int4> cur;
+    for (int b = 0; b < nbus_active; ++b) {
+        const int n = hstart[b + 1] - hstart[b];
+        if (n > 32 || n == 0) {
+            if (!cur.empty()) flush(cur);
+            cur.push_back(make_int4(-1, b, 0, -1));
+            flush(cur);
+            continue;
+        }
+        if ((int)cur.size() + n > 32) flush(cur);
+        for (int j = 0; j < n; ++j) cur.push_back(make_int4(hstart[b] + j, b, j, j == 0 ? n : 0));
+    }
+    if (!cur.empty()) flush(cur);
+    h->d.n_bus_warps = (int)(info.size() / 32);
+    return dev_upload(h, const_cast<int4 **>(&h->d.lane_info), info);
+}
+
 double elapsed_s(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return 1e-3 * ms; }
 
 }  // namespace
@@ -286,6 +310,7 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     if ((rc = dev_upload(h, const_cast<int **>(&d.hstart), hstart))) return bail(rc);
     if ((rc = dev_upload(h, const_cast<int **>(&d.gstart), gstart))) return bail(rc);
     if ((rc = dev_upload(h, &h->ref2int, ref2int))) return bail(rc);
+    if ((rc = build_bus_warps(h, hstart, nbus))) return bail(rc);
 
     {   // per line
         std::vector<double> Y(8 * (size_t)nline), xlu(8 * (size_t)nline), rate(nline);
@@ -335,7 +360,7 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
         if ((rc = dev_upload(h, const_cast<double **>(&d.Vmin), std::vector<double>(G->Vmin, G->Vmin + nbus)))) return bail(rc);
         if ((rc = dev_upload(h, const_cast<double **>(&d.Vmax), std::vector<double>(G->Vmax, G->Vmax + nbus)))) return bail(rc);
     }
-    h->max_blocks = std::max(nblocks(nbus, BBLOCK), 1024);
+    h->max_blocks = std::max(nblocks((int64_t)2 * nline + 32 * (int64_t)nbus, BBLOCK), 1024);
     if ((rc = dev_alloc(h, &d.partials, 4 * (size_t)h->max_blocks))) return bail(rc);
     if ((rc = dev_alloc(h, &d.ctrl, 1))) return bail(rc);
     if ((rc = dev_alloc(h, &d.counters, 1))) return bail(rc);
@@ -459,7 +484,7 @@ int ea_update_xbar(ea_handle_t *h) {
     if (!h) return EA_ERR_ARG;
     CK(cudaSetDevice(h->device));
     CK(cudaEventRecord(h->ev[0], h->stream));
-    k_bus<false><<<nblocks(h->nbus, BBLOCK), BBLOCK, 0, h->stream>>>(h->d, h->zsel, 0.0);
+    k_bus<false><<<nblocks((int64_t)h->d.n_bus_warps * 32, BBLOCK), BBLOCK, 0, h->stream>>>(h->d, h->zsel, 0.0);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[1], h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -557,7 +582,7 @@ static int enqueue_iteration(ea_handle *h, int max_auglag, double mu_max, double
     int rc = launch_x(h, 0, 0, max_auglag, mu_max, scale, 1, 1);
     if (rc) return rc;
     if (e) CK(cudaEventRecord(e[1], h->stream));
-    k_bus<true><<<nblocks(h->d.nbus_active, BBLOCK), BBLOCK, 0, h->stream>>>(h->d, -1, 0.0);
+    k_bus<true><<<nblocks((int64_t)h->d.n_bus_warps * 32, BBLOCK), BBLOCK, 0, h->stream>>>(h->d, -1, 0.0);
     CK(cudaGetLastError());
     h->n_bus++;
     if (h->d.partitioned && !h->loopback) {
@@ -617,6 +642,7 @@ int ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_
         if (h->kernel_timing) {
             // iterations that really ran in this chunk (later launches were no-ops)
             const int64_t ran = std::min<int64_t>(todo, h->ctrl_host->inner - (enq - todo));
+            h->n_timed += std::max<int64_t>(ran, 0);
             for (int64_t i = 0; i < ran; ++i) {
                 h->t_x += elapsed_s(h->kev[3 * i], h->kev[3 * i + 1]);
                 h->t_bus += elapsed_s(h->kev[3 * i + 1], h->kev[3 * i + 2]);
@@ -643,8 +669,12 @@ int ea_run_inner(ea_handle_t *h, int64_t outer, double beta, int64_t inner_iterl
 
 int ea_get_kernel_times(ea_handle_t *h, double out[8]) {
     if (!h || !out) return EA_ERR_ARG;
-    out[0] = h->span_s; out[1] = (double)h->n_x; out[2] = h->t_x; out[3] = (double)h->n_bus; out[4] = h->t_bus;
-    out[5] = (double)h->n_other; out[6] = 0.0; out[7] = 0.0;
+    // with kernel_timing on, [1] and [3] count the iterations the duration sums cover; the launches that found
+    // `done` set and returned at once (tail of a chunk) are reported with the other launches in [5]
+    const bool kt = h->kernel_timing && h->n_timed > 0;
+    out[0] = h->span_s; out[1] = kt ? (double)h->n_timed : (double)h->n_x; out[2] = h->t_x;
+    out[3] = kt ? (double)h->n_timed : (double)h->n_bus; out[4] = h->t_bus;
+    out[5] = (double)h->n_other + (kt ? (double)(h->n_x + h->n_bus - 2 * h->n_timed) : 0.0); out[6] = 0.0; out[7] = 0.0;
     if (h->d.count_work > 1) {      // diagnostics: x-update phase split of the LAST launch since reset (seconds)
         Counters c;
         cudaStreamSynchronize(h->stream);
@@ -818,7 +848,7 @@ int ea_reset_counters(ea_handle_t *h) {
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemset(h->d.counters, 0, sizeof(Counters)));
     { unsigned long long big = ~0ull; CK(cudaMemcpy(&h->d.counters->t[0], &big, 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(&h->d.counters->t[1], &big, 8, cudaMemcpyHostToDevice)); }
-    h->span_s = 0.0; h->n_x = h->n_bus = h->n_other = 0; h->t_x = h->t_bus = 0.0;
+    h->span_s = 0.0; h->n_x = h->n_bus = h->n_other = 0; h->t_x = h->t_bus = 0.0; h->n_timed = 0;
     return EA_OK;
 }
 
@@ -881,6 +911,7 @@ int ea_set_partition(ea_handle_t *h, int32_t rank, int32_t nranks, int64_t n_own
     d.sendbuf = h->gather_dev + (size_t)rank * stride;
     d.partitioned = 1; d.rank = rank; d.nranks = nranks; d.n_ghost = (int)n_ghost; d.stride = stride;
     d.nbus_active = (int)n_owned_bus;
+    if ((rc = build_bus_warps(h, hstart, (int)n_owned_bus))) return rc;
     h->part_rank = rank; h->part_nranks = nranks;
     h->n_owned_entries = (int64_t)h->gpad + 4 * (int64_t)owned_halves;
     h->nvar_global = nvar_global;

@@ -57,6 +57,9 @@ struct Dev {                  // everything the kernels need, passed by value
     int count_work;
     // bus-partitioned multi-GPU mode (0 / null when the handle holds the whole grid)
     int nbus_active;                      // buses this rank updates (owned buses come first); == nbus otherwise
+    int n_bus_warps;                      // bus kernel: number of warps and, per (warp, lane), the packed assignment
+    const int4 *lane_info;                // {end slot s or -1, bus, lane - leader lane, #ends of the bus if leader (0 otherwise;
+                                          //  -1: lane 0 runs the whole bus on the scalar path)}
     int partitioned, rank, nranks, n_ghost, stride;
     const int *send_pos;                  // per half-slot: position in this rank's send list, or -1
     double *sendbuf;                      // this rank's segment of `gather`: [4 partial sums | 4 doubles per send entry]
@@ -83,7 +86,7 @@ __device__ __forceinline__ void st4(double *base, int slot, const d4 &v) {
 
 // z, lambda updates (acopf_admm_update_z_gpu.jl:1-11, acopf_admm_update_l_gpu.jl:1-14)
 __device__ __forceinline__ double z_update(double lz, double l, double rho, double u, double v, double beta) {
-    return (-(lz + l + rho * (u - v))) / (beta + rho);
+    return tron::ddiv(-(lz + l + rho * (u - v)), beta + rho);      // Newton-refined reciprocal: no slow-path branch
 }
 __device__ __forceinline__ double l_update(double lz, double beta, double z) { return -(lz + beta * z); }
 
@@ -364,11 +367,158 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
 // FUSED, update_zv_kernel, update_l_kernel, compute_primal_residual_kernel,
 // vector_difference x2 and the four CUBLAS nrm2 calls
 // (acopf_admm_update_{z,l,residual}_gpu.jl).
+//
+// One LANE per branch end. The ends are stored grouped by bus, so a warp takes a run of
+// consecutive buses whose ends fill at most 32 lanes (packing precomputed on the host,
+// bw_start): loads and stores are contiguous 32-byte records, every value is read once and
+// stays in registers between the gather and the scatter. The lane of a bus's first end
+// is its leader: it adds the per-end terms of its bus IN ORDER (shuffle-down by
+// 1, 2, ...: same summation order as the reference's loops), handles the bus's
+// generators, solves the 2x2 system and broadcasts (mu1, mu2, w, theta) to its ends.
+// Buses with more than 32 ends (or none) take the scalar path on one lane.
 // ---------------------------------------------------------------------------
 constexpr int BBLOCK = 128;
 
+struct BusSolve { double mu1, mu2, wi, ti; };
+
+// gather side of one generator of the bus (acopf_bus_kernel_gpu.jl:45-63)
+__device__ __forceinline__ void bus_gen_gather(const Dev &d, const double *zold, int k, double &rhs1, double &rhs2,
+                                               double &inv_pg, double &inv_qg) {
+    const double2 u = *reinterpret_cast<const double2 *>(d.u + 2 * k);
+    const double2 z = *reinterpret_cast<const double2 *>(zold + 2 * k);
+    const double2 l = *reinterpret_cast<const double2 *>(d.l + 2 * k);
+    const double2 r = *reinterpret_cast<const double2 *>(d.rho + 2 * k);
+    const double ix = tron::ddiv(1.0, r.x), iy = tron::ddiv(1.0, r.y);
+    rhs1 += (u.x + z.x) + (l.x * ix);
+    rhs2 += (u.y + z.y) + (l.y * iy);
+    inv_pg += ix;
+    inv_qg += iy;
+}
+
+// the 2x2 solve of the bus (acopf_bus_kernel_gpu.jl:83-94)
+__device__ __forceinline__ BusSolve bus_solve(const Dev &d, int b, double common_wi, double common_ti, double inv_p,
+                                              double inv_q, double rs_w, double rs_t, double rhs1, double rhs2,
+                                              double inv_pg, double inv_qg) {
+    const double irw = tron::ddiv(1.0, rs_w);
+    common_wi *= irw;
+    const double gr = d.YshR[b], gi = d.YshI[b];
+    rhs1 -= gr * common_wi;
+    rhs2 += gi * common_wi;
+    const double A11 = (inv_pg + inv_p) + (gr * gr * irw);
+    const double A12 = -gr * (gi * irw);
+    const double A21 = A12;
+    const double A22 = (inv_qg + inv_q) + (gi * gi * irw);
+    const double iA11 = tron::ddiv(1.0, A11);
+    BusSolve s;
+    s.mu2 = tron::ddiv(rhs2 - (A21 * iA11) * rhs1, A22 - (A21 * iA11) * A12);
+    s.mu1 = (rhs1 - A12 * s.mu2) * iA11;
+    s.wi = common_wi + ((gr * s.mu1 - gi * s.mu2) * irw);
+    s.ti = tron::ddiv(common_ti, rs_t);
+    return s;
+}
+
 template <bool FUSED>
-__global__ void __launch_bounds__(BBLOCK)
+__device__ __forceinline__ void bus_gen_scatter(const Dev &d, const double *zold, double *znew, int k, const BusSolve &bs,
+                                                double beta, double (&acc)[4]) {
+    const double2 u = *reinterpret_cast<const double2 *>(d.u + 2 * k);
+    const double2 z = *reinterpret_cast<const double2 *>(zold + 2 * k);
+    const double2 l = *reinterpret_cast<const double2 *>(d.l + 2 * k);
+    const double2 r = *reinterpret_cast<const double2 *>(d.rho + 2 * k);
+    double2 v;
+    v.x = (u.x + z.x) + (l.x - bs.mu1) * tron::ddiv(1.0, r.x);
+    v.y = (u.y + z.y) + (l.y - bs.mu2) * tron::ddiv(1.0, r.y);
+    *reinterpret_cast<double2 *>(d.v + 2 * k) = v;
+    if (FUSED) {
+        const double2 lz = *reinterpret_cast<const double2 *>(d.lz + 2 * k);
+        double2 zn, ln;
+        zn.x = z_update(lz.x, l.x, r.x, u.x, v.x, beta);
+        zn.y = z_update(lz.y, l.y, r.y, u.y, v.y, beta);
+        ln.x = l_update(lz.x, beta, zn.x);
+        ln.y = l_update(lz.y, beta, zn.y);
+        *reinterpret_cast<double2 *>(znew + 2 * k) = zn;
+        *reinterpret_cast<double2 *>(d.l + 2 * k) = ln;
+        const double rpx = u.x - v.x + zn.x, rpy = u.y - v.y + zn.y;
+        const double rdx = zn.x - z.x, rdy = zn.y - z.y;
+        const double abx = rpx - zn.x, aby = rpy - zn.y;
+        acc[0] += rpx * rpx + rpy * rpy;
+        acc[1] += rdx * rdx + rdy * rdy;
+        acc[2] += zn.x * zn.x + zn.y * zn.y;
+        acc[3] += abx * abx + aby * aby;
+    }
+}
+
+// scatter side of one branch end (acopf_bus_kernel_gpu.jl:101-114) + fused z / lambda / residual terms
+template <bool FUSED>
+__device__ __forceinline__ void bus_end_scatter(const Dev &d, double *znew, int s, const d4 &u, const d4 &z, const d4 &l,
+                                                const d4 &r, double irp, double irq, const BusSolve &bs, double beta,
+                                                double (&acc)[4]) {
+    d4 v;
+    v.p = (u.p + z.p) + (l.p + bs.mu1) * irp;
+    v.q = (u.q + z.q) + (l.q + bs.mu2) * irq;
+    v.w = bs.wi;
+    v.t = bs.ti;
+    st4(d.v + d.gpad, s, v);
+    if (d.send_pos) {                      // cut-branch end: its xbar also goes into the exchange message
+        const int sp = d.send_pos[s];
+        if (sp >= 0) st4(d.sendbuf + 4, sp, v);
+    }
+    if (FUSED) {
+        const d4 lz = ld4(d.lz + d.gpad, s);
+        d4 zn, ln;
+        zn.p = z_update(lz.p, l.p, r.p, u.p, v.p, beta);
+        zn.q = z_update(lz.q, l.q, r.q, u.q, v.q, beta);
+        zn.w = z_update(lz.w, l.w, r.w, u.w, v.w, beta);
+        zn.t = z_update(lz.t, l.t, r.t, u.t, v.t, beta);
+        ln.p = l_update(lz.p, beta, zn.p);
+        ln.q = l_update(lz.q, beta, zn.q);
+        ln.w = l_update(lz.w, beta, zn.w);
+        ln.t = l_update(lz.t, beta, zn.t);
+        st4(znew + d.gpad, s, zn);
+        st4(d.l + d.gpad, s, ln);
+        const double uu[4] = { u.p, u.q, u.w, u.t }, vv[4] = { v.p, v.q, v.w, v.t };
+        const double zz[4] = { zn.p, zn.q, zn.w, zn.t }, zo[4] = { z.p, z.q, z.w, z.t };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double rp = uu[k] - vv[k] + zz[k];
+            const double rd = zz[k] - zo[k];
+            const double ab = rp - zz[k];
+            acc[0] += rp * rp; acc[1] += rd * rd; acc[2] += zz[k] * zz[k]; acc[3] += ab * ab;
+        }
+    }
+}
+
+// one whole bus on one lane (buses with > 32 ends or none)
+template <bool FUSED>
+__device__ __forceinline__ void bus_scalar(const Dev &d, const double *zold, double *znew, int b, double beta, double (&acc)[4]) {
+    const int hs = d.hstart[b], he = d.hstart[b + 1], gs = d.gstart[b], ge = d.gstart[b + 1];
+    const double *uh = d.u + d.gpad, *zh = zold + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
+    double common_wi = 0.0, common_ti = 0.0, inv_p = 0.0, inv_q = 0.0, rs_w = 0.0, rs_t = 0.0;
+    double rhs1 = 0.0, rhs2 = 0.0, inv_pg = 0.0, inv_qg = 0.0;
+    for (int k = gs; k < ge; ++k) bus_gen_gather(d, zold, k, rhs1, rhs2, inv_pg, inv_qg);
+    rhs1 -= d.pd_pu[b];
+    rhs2 -= d.qd_pu[b];
+    for (int s = hs; s < he; ++s) {
+        const d4 u = ld4(uh, s), z = ld4(zh, s), l = ld4(lh, s), r = ld4(rh, s);
+        const double irp = tron::ddiv(1.0, r.p), irq = tron::ddiv(1.0, r.q);
+        common_wi += l.w + r.w * (u.w + z.w);
+        common_ti += l.t + r.t * (u.t + z.t);
+        inv_p += irp;
+        inv_q += irq;
+        rs_w += r.w;
+        rs_t += r.t;
+        rhs1 -= (u.p + z.p) + (l.p * irp);
+        rhs2 -= (u.q + z.q) + (l.q * irq);
+    }
+    const BusSolve bs = bus_solve(d, b, common_wi, common_ti, inv_p, inv_q, rs_w, rs_t, rhs1, rhs2, inv_pg, inv_qg);
+    for (int k = gs; k < ge; ++k) bus_gen_scatter<FUSED>(d, zold, znew, k, bs, beta, acc);
+    for (int s = hs; s < he; ++s) {
+        const d4 u = ld4(uh, s), z = ld4(zh, s), l = ld4(lh, s), r = ld4(rh, s);
+        bus_end_scatter<FUSED>(d, znew, s, u, z, l, r, tron::ddiv(1.0, r.p), tron::ddiv(1.0, r.q), bs, beta, acc);
+    }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(BBLOCK, 5)
 k_bus(Dev d, int zsel_arg, double beta_arg) {
     __shared__ double red[4 * (BBLOCK / 32)];
     int zsel = zsel_arg;
@@ -380,111 +530,53 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
     }
     const double *zold = d.zbuf[zsel];
     double *znew = d.zbuf[zsel ^ 1];
-    const int b = blockIdx.x * BBLOCK + threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const int gw = (blockIdx.x * BBLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
-    if (b < d.nbus_active) {
-        const int hs = d.hstart[b], he = d.hstart[b + 1], gs = d.gstart[b], ge = d.gstart[b + 1];
-        const double *uh = d.u + d.gpad, *zh = zold + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
-        double common_wi = 0.0, common_ti = 0.0, inv_p = 0.0, inv_q = 0.0, rs_w = 0.0, rs_t = 0.0;
-        double rhs1 = 0.0, rhs2 = 0.0, inv_pg = 0.0, inv_qg = 0.0;
-        for (int k = gs; k < ge; ++k) {
-            const double2 u = *reinterpret_cast<const double2 *>(d.u + 2 * k);
-            const double2 z = *reinterpret_cast<const double2 *>(zold + 2 * k);
-            const double2 l = *reinterpret_cast<const double2 *>(d.l + 2 * k);
-            const double2 r = *reinterpret_cast<const double2 *>(d.rho + 2 * k);
-            rhs1 += (u.x + z.x) + (l.x / r.x);
-            rhs2 += (u.y + z.y) + (l.y / r.y);
-            inv_pg += 1.0 / r.x;
-            inv_qg += 1.0 / r.y;
-        }
-        rhs1 -= d.pd_pu[b];
-        rhs2 -= d.qd_pu[b];
-        for (int s = hs; s < he; ++s) {
-            const d4 u = ld4(uh, s), z = ld4(zh, s), l = ld4(lh, s), r = ld4(rh, s);
-            common_wi += l.w + r.w * (u.w + z.w);
-            common_ti += l.t + r.t * (u.t + z.t);
-            inv_p += 1.0 / r.p;
-            inv_q += 1.0 / r.q;
-            rs_w += r.w;
-            rs_t += r.t;
-            rhs1 -= (u.p + z.p) + (l.p / r.p);
-            rhs2 -= (u.q + z.q) + (l.q / r.q);
-        }
-        common_wi /= rs_w;
-        const double gr = d.YshR[b], gi = d.YshI[b];
-        rhs1 -= gr * common_wi;
-        rhs2 += gi * common_wi;
-        const double A11 = (inv_pg + inv_p) + (gr * gr / rs_w);
-        const double A12 = -gr * (gi / rs_w);
-        const double A21 = A12;
-        const double A22 = (inv_qg + inv_q) + (gi * gi / rs_w);
-        const double mu2 = (rhs2 - (A21 / A11) * rhs1) / (A22 - (A21 / A11) * A12);
-        const double mu1 = (rhs1 - A12 * mu2) / A11;
-        const double wi = common_wi + ((gr * mu1 - gi * mu2) / rs_w);
-        const double ti = common_ti / rs_t;
-
-        for (int k = gs; k < ge; ++k) {
-            const double2 u = *reinterpret_cast<const double2 *>(d.u + 2 * k);
-            const double2 z = *reinterpret_cast<const double2 *>(zold + 2 * k);
-            const double2 l = *reinterpret_cast<const double2 *>(d.l + 2 * k);
-            const double2 r = *reinterpret_cast<const double2 *>(d.rho + 2 * k);
-            double2 v;
-            v.x = (u.x + z.x) + (l.x - mu1) / r.x;
-            v.y = (u.y + z.y) + (l.y - mu2) / r.y;
-            *reinterpret_cast<double2 *>(d.v + 2 * k) = v;
-            if (FUSED) {
-                const double2 lz = *reinterpret_cast<const double2 *>(d.lz + 2 * k);
-                double2 zn, ln;
-                zn.x = z_update(lz.x, l.x, r.x, u.x, v.x, beta);
-                zn.y = z_update(lz.y, l.y, r.y, u.y, v.y, beta);
-                ln.x = l_update(lz.x, beta, zn.x);
-                ln.y = l_update(lz.y, beta, zn.y);
-                *reinterpret_cast<double2 *>(znew + 2 * k) = zn;
-                *reinterpret_cast<double2 *>(d.l + 2 * k) = ln;
-                const double rpx = u.x - v.x + zn.x, rpy = u.y - v.y + zn.y;
-                const double rdx = zn.x - z.x, rdy = zn.y - z.y;
-                const double abx = rpx - zn.x, aby = rpy - zn.y;
-                acc[0] += rpx * rpx + rpy * rpy;
-                acc[1] += rdx * rdx + rdy * rdy;
-                acc[2] += zn.x * zn.x + zn.y * zn.y;
-                acc[3] += abx * abx + aby * aby;
+    if (gw < d.n_bus_warps) {
+        const int4 info = d.lane_info[(size_t)gw * 32 + lane];      // one coalesced load, no dependent index chain
+        const int s = info.x, b = info.y, L = info.w;
+        if (__shfl_sync(full, L, 0) < 0) {                           // a bus with > 32 ends (or none): scalar path
+            if (lane == 0) bus_scalar<FUSED>(d, zold, znew, b, beta, acc);
+        } else {
+            const bool active = s >= 0;
+            const bool leader = L > 0;
+            const int sl = active ? s : 0;
+            const d4 u = ld4(d.u + d.gpad, sl), z = ld4(zold + d.gpad, sl), l = ld4(d.l + d.gpad, sl), r = ld4(d.rho + d.gpad, sl);
+            // per-end terms (acopf_bus_kernel_gpu.jl:21-43, 67-81)
+            const double t_w = l.w + r.w * (u.w + z.w);
+            const double t_t = l.t + r.t * (u.t + z.t);
+            const double t_ip = tron::ddiv(1.0, r.p), t_iq = tron::ddiv(1.0, r.q);
+            const double t_p = (u.p + z.p) + (l.p * t_ip);
+            const double t_q = (u.q + z.q) + (l.q * t_iq);
+            double common_wi = 0.0, common_ti = 0.0, inv_p = 0.0, inv_q = 0.0, rs_w = 0.0, rs_t = 0.0;
+            double rhs1 = 0.0, rhs2 = 0.0, inv_pg = 0.0, inv_qg = 0.0;
+            int gs = 0, ge = 0;
+            if (leader) {
+                gs = d.gstart[b]; ge = d.gstart[b + 1];
+                for (int k = gs; k < ge; ++k) bus_gen_gather(d, zold, k, rhs1, rhs2, inv_pg, inv_qg);
+                rhs1 -= d.pd_pu[b];
+                rhs2 -= d.qd_pu[b];
             }
-        }
-        for (int s = hs; s < he; ++s) {
-            const d4 u = ld4(uh, s), z = ld4(zh, s), l = ld4(lh, s), r = ld4(rh, s);
-            d4 v;
-            v.p = (u.p + z.p) + (l.p + mu1) / r.p;
-            v.q = (u.q + z.q) + (l.q + mu2) / r.q;
-            v.w = wi;
-            v.t = ti;
-            st4(d.v + d.gpad, s, v);
-            if (d.send_pos) {                      // cut-branch end: its xbar also goes into the exchange message
-                const int sp = d.send_pos[s];
-                if (sp >= 0) st4(d.sendbuf + 4, sp, v);
-            }
-            if (FUSED) {
-                const d4 lz = ld4(d.lz + d.gpad, s);
-                d4 zn, ln;
-                zn.p = z_update(lz.p, l.p, r.p, u.p, v.p, beta);
-                zn.q = z_update(lz.q, l.q, r.q, u.q, v.q, beta);
-                zn.w = z_update(lz.w, l.w, r.w, u.w, v.w, beta);
-                zn.t = z_update(lz.t, l.t, r.t, u.t, v.t, beta);
-                ln.p = l_update(lz.p, beta, zn.p);
-                ln.q = l_update(lz.q, beta, zn.q);
-                ln.w = l_update(lz.w, beta, zn.w);
-                ln.t = l_update(lz.t, beta, zn.t);
-                st4(znew + d.gpad, s, zn);
-                st4(d.l + d.gpad, s, ln);
-                const double uu[4] = { u.p, u.q, u.w, u.t }, vv[4] = { v.p, v.q, v.w, v.t };
-                const double zz[4] = { zn.p, zn.q, zn.w, zn.t }, zo[4] = { z.p, z.q, z.w, z.t };
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const double rp = uu[k] - vv[k] + zz[k];
-                    const double rd = zz[k] - zo[k];
-                    const double ab = rp - zz[k];
-                    acc[0] += rp * rp; acc[1] += rd * rd; acc[2] += zz[k] * zz[k]; acc[3] += ab * ab;
+            const int maxL = __reduce_max_sync(full, L);
+            for (int j = 0; j < maxL; ++j) {                     // in-order sums over the ends of each bus
+                const double a0 = __shfl_down_sync(full, t_w, j), a1 = __shfl_down_sync(full, t_t, j);
+                const double a2 = __shfl_down_sync(full, t_ip, j), a3 = __shfl_down_sync(full, t_iq, j);
+                const double a4 = __shfl_down_sync(full, r.w, j), a5 = __shfl_down_sync(full, r.t, j);
+                const double a6 = __shfl_down_sync(full, t_p, j), a7 = __shfl_down_sync(full, t_q, j);
+                if (j < L) {
+                    common_wi += a0; common_ti += a1; inv_p += a2; inv_q += a3; rs_w += a4; rs_t += a5;
+                    rhs1 -= a6; rhs2 -= a7;
                 }
             }
+            BusSolve bs = { 0.0, 0.0, 0.0, 0.0 };
+            if (leader) bs = bus_solve(d, b, common_wi, common_ti, inv_p, inv_q, rs_w, rs_t, rhs1, rhs2, inv_pg, inv_qg);
+            const int src = lane - info.z;
+            bs.mu1 = __shfl_sync(full, bs.mu1, src); bs.mu2 = __shfl_sync(full, bs.mu2, src);
+            bs.wi = __shfl_sync(full, bs.wi, src);   bs.ti = __shfl_sync(full, bs.ti, src);
+            if (leader)
+                for (int k = gs; k < ge; ++k) bus_gen_scatter<FUSED>(d, zold, znew, k, bs, beta, acc);
+            if (active) bus_end_scatter<FUSED>(d, znew, s, u, z, l, r, t_ip, t_iq, bs, beta, acc);
         }
     }
     if (FUSED) {

@@ -317,3 +317,23 @@ def test_partitioned_two_gpu_solve_matches_single_gpu():
     assert line, out.stdout[-2000:] + out.stderr[-2000:]
     res = json.loads(line[-1])
     assert res["match"], res
+
+
+def test_concurrent_scenarios_equal_their_sequential_solves():
+    """BASELINE config 5 in small: load-perturbed scenarios solved concurrently (one handle and
+    stream each) give exactly what each gives alone."""
+    from exaadmm_b200.scenarios import scenario_loads, solve_scenarios
+    d = synthetic_case(300, 40, 420, seed=300)
+    kw = dict(rho_pq=4e2, rho_va=4e4, outer_iterlim=3, inner_iterlim=300)
+    res, _ = solve_scenarios(d, range(6), **kw)
+    assert len({m.info.cumul for _, m in res}) > 1                     # the scenarios really differ
+    for s, (env, mod) in enumerate(res):
+        env1 = AdmmEnv(d, 4e2, 4e4, use_gpu=True, verbose=0)
+        m1 = ModelAcopf(env1)
+        m1.set_load(*scenario_loads(m1.grid_data, s))
+        env1.params.outer_iterlim = 3; env1.params.inner_iterlim = 300
+        admm_two_level(env1, m1, None, mode="native")
+        assert (mod.info.outer, mod.info.cumul, mod.info.status) == (m1.info.outer, m1.info.cumul, m1.info.status)
+        np.testing.assert_array_equal(mod.solution.u_curr, m1.solution.u_curr)
+        assert mod.info.objval == m1.info.objval
+        m1.close(); mod.close()
