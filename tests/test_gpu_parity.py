@@ -337,3 +337,34 @@ def test_concurrent_scenarios_equal_their_sequential_solves():
         np.testing.assert_array_equal(mod.solution.u_curr, m1.solution.u_curr)
         assert mod.info.objval == m1.info.objval
         m1.close(); mod.close()
+
+
+def test_rolling_horizon_matches_oracle_sequence(tmp_path, case9_grid):
+    """warm-started re-solves over a load profile with ramp-limited generator
+    bounds (acopf_admm_rolling_gpu.jl:16-77), against the oracle driven through the same steps."""
+    from exaadmm_b200.rolling import solve_acopf_rolling
+    rng = np.random.default_rng(9)
+    nper = 3
+    f = 1.0 + 0.03 * rng.standard_normal((case9_grid.nbus, nper)).cumsum(axis=1)
+    np.savetxt(tmp_path / "prof.Pd", case9_grid.Pd[:, None] * f)
+    np.savetxt(tmp_path / "prof.Qd", case9_grid.Qd[:, None] * f)
+    env, mod = solve_acopf_rolling(ea.CASE9, tmp_path / "prof", use_gpu=True, verbose=0, tight_factor=1.0,
+                                   outer_eps=2e-5, outer_iterlim=25, end_period=nper, result_file=str(tmp_path / "ws"))
+    par = Parameters(); par.verbose = 0; par.outer_iterlim = 25; par.outer_eps = 2e-5
+    om = OracleModel(case9_grid, par, 4e2, 4e4)
+    ramp = 0.02 * case9_grid.pgmax
+    Pd = np.loadtxt(tmp_path / "prof.Pd"); Qd = np.loadtxt(tmp_path / "prof.Qd")
+    for t in range(nper):
+        om.set_load(Pd[:, t], Qd[:, t])
+        info = om.admm_two_level()
+        got = mod.rolling_stats[t]
+        assert (got["status"] == "Solved") == (info.status == 2)
+        assert got["cumul"] == info.cumul
+        assert abs(got["objval"] - info.objval) <= 1e-6 * abs(info.objval)
+        pg = om.vec("u_curr")[0:6:2]
+        lo = np.maximum(case9_grid.pgmin, pg - ramp); hi = np.minimum(case9_grid.pgmax, pg + ramp)
+        om.L.orc_set_pg_bounds(om.h, lo.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double)),
+                               hi.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double)))
+    np.testing.assert_allclose(mod.solution.u_curr, om.vec("u_curr"), atol=1e-6, rtol=0)
+    assert (tmp_path / "ws_tight-factor1.0.txt").exists()
+    mod.close()
