@@ -368,3 +368,78 @@ def test_rolling_horizon_matches_oracle_sequence(tmp_path, case9_grid):
     np.testing.assert_allclose(mod.solution.u_curr, om.vec("u_curr"), atol=1e-6, rtol=0)
     assert (tmp_path / "ws_tight-factor1.0.txt").exists()
     mod.close()
+
+
+def test_abi_error_paths(case9_grid):
+    """Error behaviour across the ABI: negative codes + message, never an exception from C."""
+    import ctypes as C
+    from exaadmm_b200 import capi
+    from exaadmm_b200.capi import dptr
+    lib = capi.load_library()
+    env, mod = _env_mod(ea.CASE9)
+    buf = np.zeros(mod.nvar)
+    assert lib.ea_get_vector(mod.h, 99, dptr(buf), mod.nvar) == capi.EA_ERR_ARG
+    assert b"bad field" in lib.ea_last_error(mod.h)
+    assert lib.ea_get_vector(mod.h, 0, dptr(buf), mod.nvar - 1) == capi.EA_ERR_ARG
+    assert lib.ea_get_membuf(mod.h, 0, dptr(buf), 9) == capi.EA_ERR_ARG
+    assert lib.ea_set_membuf(mod.h, 3, dptr(buf), 9) == capi.EA_ERR_ARG           # staging rows are read-only
+    assert lib.ea_update_x_line(mod.h, 0, 50, 1e8, 1e-4) == capi.EA_ERR_ARG        # info.inner starts at 1
+    assert lib.ea_set_load(mod.h, dptr(buf), dptr(buf), 8) == capi.EA_ERR_ARG
+    assert lib.ea_set_option(mod.h, b"no_such_option", 1.0) == capi.EA_ERR_ARG
+    assert lib.ea_run_inner(mod.h, 0, 1e3, 10, 50, 1e8, 1e-4, 0, C.byref(C.c_int64()), dptr(buf)) == capi.EA_ERR_ARG
+    # a corrupted CSR is rejected by ea_create
+    bad = ea.GridData.from_opfdata(ea.parse_matpower(ea.CASE9))
+    bad.FrIdx = bad.FrIdx.copy(); bad.FrIdx[0] = 99
+    gs, keep = capi.make_grid_struct(bad)
+    h = C.c_void_p()
+    assert lib.ea_create(C.byref(gs), 0, C.byref(h)) == capi.EA_ERR_ARG and not h.value
+    assert lib.ea_create(C.byref(gs), 12345, C.byref(h)) == capi.EA_ERR_ARG        # device ordinal out of range
+    mod.close()
+
+
+def test_full_size_properties_activsg70k_like():
+    """BASELINE's full size (70000 / 10390 / 88207): size-independent properties after 30 fused
+    iterations - every x stays inside its box, xbar satisfies the bus balance the bus update
+    enforces, consensus entries of a bus coincide, residual vectors match their definitions."""
+    from exaadmm_b200.synthetic import named_case
+    d = named_case("ACTIVSg70k")
+    env = AdmmEnv(d, 3e4, 3e5, use_gpu=True, verbose=0, tight_factor=0.99)
+    mod = ModelAcopf(env)
+    env.params.scale = 1e-5
+    g = mod.grid_data
+    ops.admm_increment_outer(env, mod); ops.admm_outer_prestep(env, mod); ops.admm_increment_reset_inner(env, mod)
+    mod.info.inner = 0
+    env.params.inner_iterlim = 30
+    ops.admm_run_inner(env, mod)
+    assert mod.info.inner == 30 or mod.info.primres <= math.sqrt(mod.nvar) / 2500
+    u, v, z, zp = mod.solution.u_curr, mod.solution.v_curr, mod.solution.z_curr, mod.solution.z_prev
+    ng, nl = g.ngen, g.nline
+    ul = u[2 * ng:].reshape(nl, 8); vl = v[2 * ng:].reshape(nl, 8)
+    # generator boxes (acopf_generator_kernel_gpu.jl:17-21)
+    assert np.all(u[0:2 * ng:2] >= g.pgmin - 1e-12) and np.all(u[0:2 * ng:2] <= g.pgmax + 1e-12)
+    assert np.all(u[1:2 * ng:2] >= g.qgmin - 1e-12) and np.all(u[1:2 * ng:2] <= g.qgmax + 1e-12)
+    # voltage boxes and line limits of the branch solutions (w = v^2)
+    assert np.all(ul[:, 4] >= g.FrVmBound[0::2] ** 2 - 1e-9) and np.all(ul[:, 4] <= g.FrVmBound[1::2] ** 2 + 1e-9)
+    assert np.all(ul[:, 5] >= g.ToVmBound[0::2] ** 2 - 1e-9) and np.all(ul[:, 5] <= g.ToVmBound[1::2] ** 2 + 1e-9)
+    viol = np.maximum(ul[:, 0] ** 2 + ul[:, 1] ** 2, ul[:, 2] ** 2 + ul[:, 3] ** 2) - g.rateA
+    assert np.quantile(viol, 0.999) <= 1e-5                      # AL loop drives the limit violation to ~1e-6
+    # bus balance of xbar: sum pg - Pd - sum p_ij - sum p_ji - YshR * w = 0 (acopf_bus_kernel_gpu.jl:83-94)
+    fb = g.brBusIdx[0::2] - 1; tb = g.brBusIdx[1::2] - 1
+    gen_bus = np.empty(ng, dtype=np.int64)
+    for b in range(g.nbus):
+        gen_bus[g.GenIdx[g.GenStart[b] - 1:g.GenStart[b + 1] - 1] - 1] = b
+    wbus = np.zeros(g.nbus); wbus[fb] = vl[:, 4]
+    balp = np.bincount(gen_bus, weights=v[0:2 * ng:2], minlength=g.nbus) - g.Pd / g.baseMVA \
+        - np.bincount(fb, weights=vl[:, 0], minlength=g.nbus) - np.bincount(tb, weights=vl[:, 2], minlength=g.nbus) - g.YshR * wbus
+    balq = np.bincount(gen_bus, weights=v[1:2 * ng:2], minlength=g.nbus) - g.Qd / g.baseMVA \
+        - np.bincount(fb, weights=vl[:, 1], minlength=g.nbus) - np.bincount(tb, weights=vl[:, 3], minlength=g.nbus) + g.YshI * wbus
+    assert np.abs(balp).max() <= 1e-9 and np.abs(balq).max() <= 1e-9
+    # all ends at a bus share w and theta
+    wb = np.full(g.nbus, np.nan); wb[fb] = vl[:, 4]
+    assert np.nanmax(np.abs(wb[tb] - vl[:, 5])[~np.isnan(wb[tb])]) == 0.0
+    # residual vectors
+    np.testing.assert_allclose(mod.solution.rp, u - v + z, atol=1e-12)
+    np.testing.assert_allclose(mod.solution.rd, z - zp, atol=1e-12)
+    assert mod.info.primres == pytest.approx(np.linalg.norm(u - v + z), rel=1e-12)
+    assert mod.info.mismatch == pytest.approx(np.linalg.norm(u - v), rel=1e-10)
+    mod.close()
