@@ -939,7 +939,9 @@ int ea_comm_init(ea_handle_t *h, const char *nccl_lib, const char id[128]) {
     memcpy(&uid, id, 128);
     ncclResult_t r = g_nccl.CommInitRank(&h->comm, h->part_nranks, uid, h->part_rank);
     if (r != ncclSuccess) return fail(h, EA_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
-    return EA_OK;
+    // first collective = connection set-up (hundreds of ms): pay it here, not inside the solve
+    double warm = 0.0;
+    return allgather_scalar_sum(h, 0.0, &warm);
 }
 
 // Loopback exchange for single-GPU tests: the caller moves the message through the host.
