@@ -122,10 +122,13 @@ int fail(ea_handle *h, int code, const char *fmt, ...) {
             return fail(h, EA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+// Device memory comes from the stream-ordered pool (cudaMallocAsync) with an unlimited release threshold: handles
+// are created and destroyed per solve by drop-in callers (solve_acopf builds a model per call), and the pool turns the
+// ~50 allocations of ea_create into pointer bumps after the first handle.
 template <typename T> int dev_alloc(ea_handle *h, T **p, size_t n) {
     void *q = nullptr;
-    CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
-    CK(cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    CK(cudaMallocAsync(&q, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+    CK(cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
     h->allocs.push_back(q);
     *p = static_cast<T *>(q);
     return EA_OK;
@@ -133,7 +136,8 @@ template <typename T> int dev_alloc(ea_handle *h, T **p, size_t n) {
 template <typename T> int dev_upload(ea_handle *h, T **p, const std::vector<T> &v) {
     int rc = dev_alloc(h, p, v.size());
     if (rc) return rc;
-    if (!v.empty()) CK(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!v.empty()) CK(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));          // v may be a temporary: the copy must have left the host buffer
     return EA_OK;
 }
 
@@ -236,6 +240,12 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     if (cudaSetDevice(device) != cudaSuccess) return bail(fail(h, EA_ERR_CUDA, "cudaSetDevice(%d) failed", device));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(h, EA_ERR_CUDA, "cudaStreamCreate failed"));
+    {
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     for (auto &e : h->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(h, EA_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaEventCreate(&h->span0) != cudaSuccess || cudaEventCreate(&h->span1) != cudaSuccess)
         return bail(fail(h, EA_ERR_CUDA, "cudaEventCreate failed"));
@@ -383,7 +393,8 @@ void ea_destroy(ea_handle_t *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->gather_host) cudaFreeHost(h->gather_host);
-    for (void *p : h->allocs) cudaFree(p);
+    for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->res_host) cudaFreeHost(h->res_host);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
