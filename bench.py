@@ -174,9 +174,11 @@ def run_ours(args, rank, world, local_rank):
     grid, _ = make_grid(args.workload)
     par, rho_pq, rho_va = default_params(args.workload)
     if world > 1:
-        # scenario sharding: rank r solves load scenario r (loads scaled by U[0.95,1.05], seed nbus + r)
+        # scenario sharding: rank r solves load scenario r: every (Pd, Qd) scaled by iid U[0.99, 1.01], seed nbus + r.
+        # (+-5 % per bus, the spread SURVEY 8d suggests, makes this synthetic grid stall - 20 x 1000 iterations without
+        #  converging, oracle and GPU alike - while +-1 % converges like the base case: 12 outer / 447 inner iterations.)
         rng = np.random.default_rng(grid.nbus + rank)
-        f = rng.uniform(0.95, 1.05, grid.nbus)
+        f = rng.uniform(0.99, 1.01, grid.nbus)
         grid.Pd = grid.Pd * f
         grid.Qd = grid.Qd * f
     nvar = 2 * grid.ngen + 8 * grid.nline
@@ -374,7 +376,7 @@ def run_ours(args, rank, world, local_rank):
                    "nbus": grid.nbus, "ngen": grid.ngen, "nline": grid.nline, "nvar": nvar, "rho_pq": rho_pq,
                    "rho_va": rho_va, "scale": par.scale, "obj_scale": par.obj_scale, "tight_factor": 0.99,
                    "outer_iterlim": 20, "inner_iterlim": 1000,
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent load scenarios, one per GPU",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent load scenarios (loads x U[0.99,1.01]), one per GPU, no collective",
                    "l2_policy": "working set (15 vectors x 5.8 MB + grid) is below the 126 MB L2; iterations are "
                                 "data-dependent (each reads what the previous wrote), no artificial flush",
                    "restarts_in_timed_region": A["restarts"]},
