@@ -143,6 +143,8 @@ SIGNATURES = {
                                    C.c_int64, C.c_int64]),
     "ea_nccl_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "ea_comm_init": (C.c_int, [_H, C.c_char_p, C.c_char_p]),
+    "ea_peer_export": (C.c_int, [_H, C.c_char_p]),
+    "ea_peer_import": (C.c_int, [_H, C.c_char_p]),
     "ea_part_begin": (C.c_int, [_H, C.c_int64, C.c_double, C.c_int32, C.c_double, C.c_double]),
     "ea_part_get_message": (C.c_int, [_H, _pd, C.c_int64]),
     "ea_part_put_gathered": (C.c_int, [_H, _pd, C.c_int64]),

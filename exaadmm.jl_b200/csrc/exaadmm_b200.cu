@@ -67,6 +67,8 @@ struct ea_handle {
     double *gather_host = nullptr;              // pinned mirror (scalar collectives, loopback tests)
     ncclComm_t comm = nullptr;
     void *nccl_lib = nullptr;
+    double *xbuf = nullptr;                     // cudaMalloc'ed exchange buffer (IPC-exported), peer mode
+    std::vector<void *> peer_maps;              // cudaIpcOpenMemHandle'd peers
     std::string err;
 };
 
@@ -392,6 +394,8 @@ void ea_destroy(ea_handle_t *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (void *p : h->peer_maps) if (p) cudaIpcCloseMemHandle(p);
+    if (h->xbuf) cudaFree(h->xbuf);
     if (h->gather_host) cudaFreeHost(h->gather_host);
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -598,9 +602,11 @@ static int enqueue_iteration(ea_handle *h, int max_auglag, double mu_max, double
     h->n_bus++;
     if (h->d.partitioned && !h->loopback) {
         // the one exchange of the iteration: xbar halves of the cut-branch ends + residual partial sums
-        if (!h->comm) return fail(h, EA_ERR_STATE, "partitioned handle without a communicator (call ea_comm_init)");
-        ncclResult_t r = g_nccl.AllGather(h->d.sendbuf, h->gather_dev, (size_t)h->d.stride, ncclDouble, h->comm, h->stream);
-        if (r != ncclSuccess) return fail(h, EA_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+        if (!h->d.peer_mode) {
+            if (!h->comm) return fail(h, EA_ERR_STATE, "partitioned handle without a communicator (call ea_comm_init)");
+            ncclResult_t r = g_nccl.AllGather(h->d.sendbuf, h->gather_dev, (size_t)h->d.stride, ncclDouble, h->comm, h->stream);
+            if (r != ncclSuccess) return fail(h, EA_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+        }   // peer mode: the bus kernel has already stored the segment into the peers' buffers
         k_finish<<<1, FBLOCK, 0, h->stream>>>(h->d);
         CK(cudaGetLastError());
         h->n_other++;
@@ -953,6 +959,49 @@ int ea_comm_init(ea_handle_t *h, const char *nccl_lib, const char id[128]) {
     // first collective = connection set-up (hundreds of ms): pay it here, not inside the solve
     double warm = 0.0;
     return allgather_scalar_sum(h, 0.0, &warm);
+}
+
+// Peer-memory exchange: export this rank's exchange buffer (CUDA IPC), import everybody's, switch the fused loop
+// from ncclAllGather to direct NVLink stores + flags (see k_bus / k_finish). ea_comm_init is still needed for the
+// handful of scalar collectives outside the inner loop.
+int ea_peer_export(ea_handle_t *h, char out[64]) {
+    if (!h || !out) return EA_ERR_ARG;
+    if (!h->d.partitioned) return fail(h, EA_ERR_STATE, "ea_peer_export: call ea_set_partition first");
+    CK(cudaSetDevice(h->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+    if (!h->xbuf) {
+        const size_t bytes = sizeof(double) * 2 * (size_t)h->part_nranks * h->d.stride + sizeof(unsigned long long) * 2 * (size_t)h->part_nranks;
+        CK(cudaMalloc((void **)&h->xbuf, bytes));
+        CK(cudaMemset(h->xbuf, 0, bytes));
+        CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->xbuf));
+    memcpy(out, &mh, 64);
+    return EA_OK;
+}
+
+int ea_peer_import(ea_handle_t *h, const char *handles /* nranks x 64 bytes, rank order */) {
+    if (!h || !handles) return EA_ERR_ARG;
+    if (!h->d.partitioned || !h->xbuf) return fail(h, EA_ERR_STATE, "ea_peer_import: call ea_peer_export first");
+    CK(cudaSetDevice(h->device));
+    std::vector<double *> bases((size_t)h->part_nranks, nullptr);
+    for (int r = 0; r < h->part_nranks; ++r) {
+        if (r == h->part_rank) { bases[r] = h->xbuf; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handles + 64 * (size_t)r, 64);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_maps.push_back(p);
+        bases[r] = static_cast<double *>(p);
+    }
+    double **dev_bases = nullptr;
+    int rc = dev_upload(h, &dev_bases, bases);
+    if (rc) return rc;
+    h->d.peer_base = dev_bases;
+    h->d.xbase = h->xbuf;
+    h->d.peer_mode = 1;
+    return EA_OK;
 }
 
 // Loopback exchange for single-GPU tests: the caller moves the message through the host.

@@ -29,6 +29,7 @@ struct Ctrl {                 // device-resident loop control (one per handle)
     int zsel;                 // which of the two z buffers is z_curr
     unsigned ticket;          // last-block election for the residual reduction
     int next_line;            // work queue head of the branch kernel (reset for the next x-update)
+    unsigned long long seq;   // partitioned iterations executed since the handle was created (exchange stamps / parity)
 };
 
 struct Counters { unsigned long long v[8]; unsigned long long t[4]; };   // t: first start, queue empty, last end (globaltimer ns), launches
@@ -66,7 +67,20 @@ struct Dev {                  // everything the kernels need, passed by value
     const double *gather;                 // nranks x stride, filled by the all-gather
     const int *ghost_slot;                // half-slot of every ghost end
     const int *ghost_src;                 // index of its xbar record in `gather`
+    // peer-memory exchange (NVLink, CUDA IPC): instead of the all-gather, the last block of the bus kernel stores this
+    // rank's segment straight into every peer's buffer and raises a flag there; k_finish waits on its own flags.
+    // Buffer of every rank: [2 parities][nranks x stride doubles] then [2][nranks] 64-bit stamps.
+    int peer_mode;
+    double *xbase;                        // this rank's exchange buffer
+    double *const *peer_base;             // device array: every rank's buffer as mapped into this process
 };
+
+__device__ __forceinline__ double *xseg(const Dev &d, double *base, int parity, int r) {
+    return base + ((size_t)parity * d.nranks + r) * d.stride;
+}
+__device__ __forceinline__ unsigned long long *xflag(const Dev &d, double *base, int parity, int r) {
+    return reinterpret_cast<unsigned long long *>(base + (size_t)2 * d.nranks * d.stride) + parity * d.nranks + r;
+}
 
 // ---------------------------------------------------------------------------
 // small device helpers
@@ -460,7 +474,7 @@ __device__ __forceinline__ void bus_end_scatter(const Dev &d, double *znew, int 
     st4(d.v + d.gpad, s, v);
     if (d.send_pos) {                      // cut-branch end: its xbar also goes into the exchange message
         const int sp = d.send_pos[s];
-        if (sp >= 0) st4(d.sendbuf + 4, sp, v);
+        if (sp >= 0) st4((d.peer_mode ? xseg(d, d.xbase, (int)(d.ctrl->seq & 1ull), d.rank) : d.sendbuf) + 4, sp, v);
     }
     if (FUSED) {
         const d4 lz = ld4(d.lz + d.gpad, s);
@@ -581,7 +595,27 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
     }
     if (FUSED) {
         const bool last = grid_sum4<BBLOCK>(acc, d.partials, &d.ctrl->ticket, red);
-        if (last && threadIdx.x == 0 && d.partitioned) {
+        if (last && d.partitioned && d.peer_mode) {
+            // fused exchange: this block is the last one of the kernel, the whole segment (xbar halves written by all
+            // blocks + the 4 partial sums) is complete -> store it into every peer's buffer over NVLink, then raise
+            // this rank's flag there (stamp = iteration sequence number)
+            const unsigned long long seq = d.ctrl->seq;
+            const int par = (int)(seq & 1ull);
+            double *seg = xseg(d, d.xbase, par, d.rank);
+            if (threadIdx.x < 4) seg[threadIdx.x] = acc[threadIdx.x];
+            __syncthreads();
+            for (int i = threadIdx.x; i < d.stride; i += BBLOCK) {
+                const double v = __ldcg(seg + i);
+                for (int r = 0; r < d.nranks; ++r)
+                    if (r != d.rank) xseg(d, d.peer_base[r], par, d.rank)[i] = v;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x < d.nranks && threadIdx.x != d.rank) {
+                unsigned long long *f = xflag(d, d.peer_base[threadIdx.x], par, d.rank);
+                asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(seq + 1ull) : "memory");
+            }
+        } else if (last && threadIdx.x == 0 && d.partitioned) {
             // partial sums over this rank's entries; norms and the termination test follow the all-gather (k_finish)
 #pragma unroll
             for (int k = 0; k < 4; ++k) d.sendbuf[k] = acc[k];
@@ -610,10 +644,25 @@ __global__ void __launch_bounds__(FBLOCK) k_finish(Dev d) {
     const double beta = c->beta;
     const double *zold = d.zbuf[zsel];
     double *znew = d.zbuf[zsel ^ 1];
+    const unsigned long long seq = c->seq;
+    const double *gather = d.gather;
+    if (d.peer_mode) {
+        const int par = (int)(seq & 1ull);
+        gather = xseg(d, d.xbase, par, 0);
+        if (threadIdx.x < d.nranks && threadIdx.x != d.rank) {           // wait for every peer's segment of this iteration
+            const unsigned long long *f = xflag(d, d.xbase, par, threadIdx.x);
+            unsigned long long got;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(f) : "memory");
+                if (got < seq + 1ull) __nanosleep(64);
+            } while (got < seq + 1ull);
+        }
+        __syncthreads();
+    }
     for (int g = threadIdx.x; g < d.n_ghost; g += FBLOCK) {
         const int s = d.ghost_slot[g];
-        const double *src = d.gather + d.ghost_src[g];
-        d4 v; v.p = src[0]; v.q = src[1]; v.w = src[2]; v.t = src[3];
+        const double *src = gather + d.ghost_src[g];
+        d4 v; v.p = __ldcg(src); v.q = __ldcg(src + 1); v.w = __ldcg(src + 2); v.t = __ldcg(src + 3);
         st4(d.v + d.gpad, s, v);
         const d4 u = ld4(d.u + d.gpad, s), l = ld4(d.l + d.gpad, s), r = ld4(d.rho + d.gpad, s), lz = ld4(d.lz + d.gpad, s);
         d4 zn, ln;
@@ -629,13 +678,14 @@ __global__ void __launch_bounds__(FBLOCK) k_finish(Dev d) {
         double tot[4] = { 0.0, 0.0, 0.0, 0.0 };
         for (int r = 0; r < d.nranks; ++r)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tot[k] += d.gather[(size_t)r * d.stride + k];
+            for (int k = 0; k < 4; ++k) tot[k] += __ldcg(gather + (size_t)r * d.stride + k);
 #pragma unroll
         for (int k = 0; k < 4; ++k) c->res[k] = sqrt(tot[k]);
         const long long inner = c->inner + 1;
         c->inner = inner;
         c->zsel = zsel ^ 1;
         c->next_line = 0;
+        c->seq = seq + 1ull;
         if (c->res[0] <= c->eps_pri || inner >= c->inner_limit) c->done = 1;
     }
     (void)zold;

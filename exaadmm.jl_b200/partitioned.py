@@ -66,9 +66,21 @@ def init_comm(mod: ModelAcopf, rank: int, nccl_lib: str | None = None) -> None:
     mod._check(lib.ea_comm_init(mod.h, path, box[0]))
 
 
+def init_peer_exchange(mod: ModelAcopf) -> None:
+    """Switch the per-iteration exchange from ncclAllGather to direct peer-memory stores (CUDA IPC over
+    NVLink): all-gather the 64-byte IPC handles of the ranks' exchange buffers and import them."""
+    import torch.distributed as dist
+    buf = C.create_string_buffer(64)
+    mod._check(mod.lib.ea_peer_export(mod.h, buf))
+    handles = [None] * dist.get_world_size()
+    dist.all_gather_object(handles, bytes(buf.raw))
+    mod._check(mod.lib.ea_peer_import(mod.h, b"".join(handles)))
+    dist.barrier()
+
+
 def solve_acopf_partitioned(case, rank: int, world: int, *, outer_iterlim=20, inner_iterlim=1000, rho_pq=400.0,
                             rho_va=40000.0, obj_scale=1.0, scale=1e-4, tight_factor=1.0, outer_eps=2e-4, gpu_no=None,
-                            verbose=0, part: np.ndarray | None = None):
+                            verbose=0, part: np.ndarray | None = None, exchange: str = "peer"):
     """`solve_acopf` for one case split over `world` GPUs (call from every rank of an
     initialised torch.distributed job). Returns (env, mod, local_grid); `mod.info` holds the
     global iteration counts / residuals / objective on every rank, `mod.solution.*` the
@@ -80,6 +92,8 @@ def solve_acopf_partitioned(case, rank: int, world: int, *, outer_iterlim=20, in
         part = partition_buses(grid, world)
     mod, lg = make_partitioned_model(env, grid, part, rank)
     init_comm(mod, rank)
+    if exchange == "peer":
+        init_peer_exchange(mod)
     p = env.params
     p.scale, p.obj_scale, p.outer_eps, p.outer_iterlim, p.inner_iterlim = scale, obj_scale, outer_eps, outer_iterlim, inner_iterlim
     p.verbose = verbose if rank == 0 else 0

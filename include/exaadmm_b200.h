@@ -241,6 +241,12 @@ int  ea_set_partition(ea_handle_t *h, int32_t rank, int32_t nranks, int64_t n_ow
  * calls ea_comm_init. */
 int  ea_nccl_unique_id(const char *nccl_lib, char out[128]);
 int  ea_comm_init(ea_handle_t *h, const char *nccl_lib, const char id[128]);
+/* Peer-memory exchange (one node, NVLink/NVSwitch): every rank exports its exchange buffer as a CUDA IPC handle
+ * (64 bytes), the caller all-gathers the handles (rank order) and every rank imports them. From then on the
+ * fused loop does NOT call NCCL: the last block of the bus kernel stores this rank's segment into every peer's
+ * buffer and raises a flag there; k_finish waits on its own flags (double-buffered by iteration parity). */
+int  ea_peer_export(ea_handle_t *h, char out[64]);
+int  ea_peer_import(ea_handle_t *h, const char *handles);
 /* Loopback form of one partitioned iteration for single-GPU tests (the caller carries the
  * message through the host): begin = x-update + bus kernel; get_message = this rank's
  * segment (stride = 4 + 4*max_send doubles); put_gathered = all nranks segments;

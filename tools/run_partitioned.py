@@ -29,24 +29,28 @@ if len(sys.argv) > 3:                      # optional rho override: workload rho
 kw = dict(rho_pq=rho_pq, rho_va=rho_va, scale=par.scale, tight_factor=0.99, outer_iterlim=20, inner_iterlim=1000)
 grid = ea.GridData.from_opfdata(data, tight_factor=0.99)
 part = partition_buses(grid, world)
-for rep in range(2):
+results = {}
+for exchange in ("nccl", "peer"):
+  for rep in range(2):
     dist.barrier(); t0 = time.perf_counter()
-    env, mod, lg = solve_acopf_partitioned(data, rank, world, part=part, **kw)
+    env, mod, lg = solve_acopf_partitioned(data, rank, world, part=part, exchange=exchange, **kw)
     torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
     info = mod.info
     res = dict(status=info.status, outer=info.outer, cumul=info.cumul, objval=info.objval, mismatch=info.mismatch,
                solver_s=info.time_overall, wall_s=dt)
+    results[exchange] = res
     mod.close()
 if rank == 0:
-    out = {"workload": wl, "n_gpus": world, "partition": cut_statistics(grid, part), "partitioned": res}
+    out = {"workload": wl, "n_gpus": world, "partition": cut_statistics(grid, part), "partitioned": res,
+           "partitioned_nccl_allgather": results["nccl"], "partitioned_peer_stores": results["peer"]}
     t0 = time.perf_counter()
     env1, mod1 = solve_acopf(data, use_gpu=True, verbose=0, mode="native", **kw)
     env1, mod1 = solve_acopf(data, use_gpu=True, verbose=0, mode="native", **kw)
     i1 = mod1.info
     out["single_gpu"] = dict(status=i1.status, outer=i1.outer, cumul=i1.cumul, objval=i1.objval, mismatch=i1.mismatch,
                              solver_s=i1.time_overall)
-    out["match"] = bool(i1.status == res["status"] and i1.outer == res["outer"] and i1.cumul == res["cumul"]
-                        and abs(i1.objval - res["objval"]) <= 1e-9 * abs(i1.objval))
+    out["match"] = all(bool(i1.status == r["status"] and i1.outer == r["outer"] and i1.cumul == r["cumul"]
+                            and abs(i1.objval - r["objval"]) <= 1e-9 * abs(i1.objval)) for r in results.values())
     print(json.dumps(out))
 dist.barrier()
 dist.destroy_process_group()

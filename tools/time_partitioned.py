@@ -8,7 +8,7 @@ import bench, exaadmm_b200 as ea
 from exaadmm_b200.capi import dptr
 from exaadmm_b200.environment import AdmmEnv
 from exaadmm_b200.partition import partition_buses
-from exaadmm_b200.partitioned import make_partitioned_model, init_comm
+from exaadmm_b200.partitioned import make_partitioned_model, init_comm, init_peer_exchange
 
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
 wl = sys.argv[1] if len(sys.argv) > 1 else "ACTIVSg70k"
@@ -19,6 +19,8 @@ env = AdmmEnv(data, rho_pq, rho_va, use_gpu=True, tight_factor=0.99, gpu_no=loca
 grid = ea.GridData.from_opfdata(data, tight_factor=0.99)
 mod, lg = make_partitioned_model(env, grid, partition_buses(grid, world), rank)
 init_comm(mod, rank)
+if len(sys.argv) > 2 and sys.argv[2] == 'peer':
+    init_peer_exchange(mod)
 lib, h = mod.lib, mod.h
 lib.ea_set_option(h, b"count_work", 0.0)
 res = np.zeros(4); got = C.c_int64(); nz = C.c_double()
