@@ -61,6 +61,17 @@ enum ea_field {
     EA_NUM_FIELDS = 15
 };
 
+/* Multi-period model: the ramp-coupling vectors of period t >= 2, one entry per generator
+ * (SolutionRamping, src/models/mpacopf/mpacopf_model.jl:1-16). */
+enum ea_ramp_field {
+    EA_RAMP_U_CURR = 0,   /* phat_{t-1}: period t's copy of the previous period's pg */
+    EA_RAMP_V_CURR = 1,   /* allocated by the reference, never used (the consensus value is v_curr[pg] of period t-1) */
+    EA_RAMP_L_CURR = 2, EA_RAMP_RHO = 3, EA_RAMP_RD = 4, EA_RAMP_RP = 5, EA_RAMP_Z_OUTER = 6,
+    EA_RAMP_Z_CURR = 7, EA_RAMP_Z_PREV = 8, EA_RAMP_LZ = 9, EA_RAMP_AX_PLUS_BY = 10,
+    EA_RAMP_S_CURR = 11,  /* s_t = pg_t - phat_{t-1}, |s_t| <= ramp_rate */
+    EA_RAMP_NUM_FIELDS = 12
+};
+
 /* GridData as consumed by the hot path (src/utils/grid_data.jl:61-83,
  * src/utils/opfdata.jl:542-831). Lengths in comments. */
 typedef struct ea_grid {

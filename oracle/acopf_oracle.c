@@ -22,23 +22,7 @@
 #include <omp.h>
 #endif
 
-#define NV 6          /* branch sub-problem size with line limits (acopf_model.jl:46) */
-#define MEMROWS 31    /* acopf_model.jl:87 */
-
-struct orc_model {
-    int64_t ngen, nline, nbus, nvar;
-    double baseMVA;
-    double *pgmin, *pgmax, *qgmin, *qgmax, *c2, *c1, *c0, *pgmin_curr, *pgmax_curr;
-    double *YshR, *YshI, *Y[8];
-    double *FrVmBound, *ToVmBound, *FrVaBound, *ToVaBound, *rateA;
-    int64_t *FrStart, *FrIdx, *ToStart, *ToIdx, *GenStart, *GenIdx, *brBusIdx; /* 0-based */
-    double *Pd, *Qd, *Vmin, *Vmax;
-    double *vec[EA_NUM_FIELDS];
-    double *membuf;
-    int nthreads;
-    ea_counters_t cnt;
-    int32_t *eval_trace;   /* optional: per-line evaluation count of the last x-update (diagnostics) */
-};
+#include "oracle_internal.h"
 
 /* ------------------------------------------------------------------------ */
 /* small helpers                                                            */
@@ -201,7 +185,6 @@ void orc_eval_gh(const double x[6], const double *p, const double Y[8], double s
 /* ------------------------------------------------------------------------ */
 /* TRON (dense n x n, n <= NV)                          */
 /* ------------------------------------------------------------------------ */
-typedef struct { int64_t nfev, ngev, cg, shifts, rejected; } tron_stats_t;
 
 static void symv(int n, const double *A, int lda, const double *x, double *y) {
     for (int i = 0; i < n; ++i) {
@@ -463,16 +446,14 @@ static void dspcg(int n, double *x, const double *xl, const double *xu, const do
 
 /* B.0 driver: acopf_tron_linelimit_kernel.jl:44-148 around ExaTron.dtron,
  * == ExaTron.solveProblem on the CPU path (acopf_auglag_linelimit_kernel_cpu.jl:104-117). */
-static int tron_solve(double x[NV], const double xl[NV], const double xu[NV], const double *param,
-                      const double Y[8], double scale, int max_feval, int max_minor, double gtol,
-                      int *minor_out, tron_stats_t *st) {
-    const int n = NV;
+int orc__tron_cb(int n, double *x, const double *xl, const double *xu, orc__f_fn evalf, orc__gh_fn evalgh,
+                 const void *ctx, int max_feval, int max_minor, double gtol, int *minor_out, tron_stats_t *st) {
     const double eta0 = 1e-4, eta1 = 0.25, eta2 = 0.75, sigma1 = 0.25, sigma2 = 0.5, sigma3 = 4.0;
     const double frtol = 1e-12, fatol = 0.0, fmin = -1e32, cgtol = 0.1;
     const int cg_itermax = n;
     double g[NV], A[NV * NV], s[NV], xc[NV], wa[NV];
-    double f = orc_eval_f(x, param, Y, scale);
-    orc_eval_gh(x, param, Y, scale, g, A);
+    double f = evalf(x, ctx);
+    evalgh(x, ctx, g, A);
     int nfev = 1, minor = 1, iter = 1, status = 0;
     st->nfev++; st->ngev++;
     double delta = nrm2(n, g), alphac = 1.0;
@@ -480,12 +461,12 @@ static int tron_solve(double x[NV], const double xl[NV], const double xu[NV], co
         int task; /* 1 F, 2 GH, 4 CONV, 10 WARN */
         do {
             const double fc = f;
-            memcpy(xc, x, sizeof(xc));
+            memcpy(xc, x, sizeof(double) * (size_t)n);
             alphac = dcauchy(n, x, xl, xu, A, g, delta, alphac, s);
             dspcg(n, x, xl, xu, A, g, delta, cgtol, s, cg_itermax, st);
             symv(n, A, NV, s, wa);
             const double prered = -(dot(n, s, g) + 0.5 * dot(n, s, wa));
-            f = orc_eval_f(x, param, Y, scale);
+            f = evalf(x, ctx);
             nfev++; st->nfev++;
             if (nfev >= max_feval) { *minor_out = minor; return status; }
             const double actred = fc - f;
@@ -500,19 +481,36 @@ static int tron_solve(double x[NV], const double xl[NV], const double xu[NV], co
             else if (actred < eta2 * prered) delta = dmax(sigma1 * delta, dmin(alpha * snorm, sigma3 * delta));
             else delta = dmax(delta, dmin(alpha * snorm, sigma3 * delta));
             if (actred > eta0 * prered) { task = 2; iter++; }
-            else { task = 1; memcpy(x, xc, sizeof(xc)); f = fc; st->rejected++; }
+            else { task = 1; memcpy(x, xc, sizeof(double) * (size_t)n); f = fc; st->rejected++; }
             if (f < fmin) task = 10;
             if (fabs(actred) <= fatol && prered <= fatol) task = 4;
             if (fabs(actred) <= frtol * fabs(f) && prered <= frtol * fabs(f)) task = 4;
         } while (task == 1);
         if (task == 4 || task == 10) break;
-        orc_eval_gh(x, param, Y, scale, g, A);
+        evalgh(x, ctx, g, A);
         minor++; st->ngev++;
         if (dgpnorm(n, x, xl, xu, g) <= gtol) break;
         if (minor >= max_minor) { status = 1; break; }
     }
     *minor_out = minor;
     return status;
+}
+
+/* the branch instance of the driver: objective of acopf_eval_linelimit_kernel_cpu.jl */
+typedef struct { const double *param, *Y; double scale; } branch_ctx_t;
+static double branch_f(const double *x, const void *c) {
+    const branch_ctx_t *b = (const branch_ctx_t *)c;
+    return orc_eval_f(x, b->param, b->Y, b->scale);
+}
+static void branch_gh(const double *x, const void *c, double *g, double *A) {
+    const branch_ctx_t *b = (const branch_ctx_t *)c;
+    orc_eval_gh(x, b->param, b->Y, b->scale, g, A);
+}
+static int tron_solve(double x[NV], const double xl[NV], const double xu[NV], const double *param,
+                      const double Y[8], double scale, int max_feval, int max_minor, double gtol,
+                      int *minor_out, tron_stats_t *st) {
+    const branch_ctx_t ctx = { param, Y, scale };
+    return orc__tron_cb(NV, x, xl, xu, branch_f, branch_gh, &ctx, max_feval, max_minor, gtol, minor_out, st);
 }
 
 int orc_tron_solve(double x[6], const double xl[6], const double xu[6], const double *param,

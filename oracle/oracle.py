@@ -26,8 +26,8 @@ _pd = C.POINTER(C.c_double)
 
 
 def build(force: bool = False) -> Path:
-    src = _HERE / "acopf_oracle.c"
-    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+    newest = max(f.stat().st_mtime for f in list(_HERE.glob("*.c")) + list(_HERE.glob("*.h")))
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
         subprocess.run(["make", "-C", str(_HERE)] + (["-B"] if force else []), check=True,
                        stdout=subprocess.DEVNULL)
     return LIB_PATH
@@ -81,6 +81,33 @@ def lib():
         L.orc_tron_solve.argtypes = [_pd, _pd, _pd, _pd, _pd, C.c_double, C.c_int, C.c_int, C.c_double,
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_tron_solve.restype = C.c_int
+        # multi-period model (mpacopf_oracle.h)
+        L.orc_mp_create.argtypes = [C.POINTER(EaGrid), C.c_int32, _pd, _pd, C.c_double, C.POINTER(H)]
+        L.orc_mp_create.restype = C.c_int
+        L.orc_mp_destroy.argtypes = [H]
+        L.orc_mp_set_threads.argtypes = [H, C.c_int]
+        L.orc_mp_period.argtypes = [H, C.c_int32]
+        L.orc_mp_period.restype = H
+        L.orc_mp_ramp_vector.argtypes = [H, C.c_int32, C.c_int]
+        L.orc_mp_ramp_vector.restype = _pd
+        L.orc_mp_gen_membuf.argtypes = [H, C.c_int32]
+        L.orc_mp_gen_membuf.restype = _pd
+        L.orc_mp_nvar.argtypes = [H]
+        L.orc_mp_nvar.restype = C.c_int64
+        L.orc_mp_init_solution.argtypes = [H, C.c_double, C.c_double]
+        L.orc_mp_outer_prestep.argtypes = [H]
+        L.orc_mp_outer_prestep.restype = C.c_double
+        L.orc_mp_inner_prestep.argtypes = [H]
+        L.orc_mp_update_x.argtypes = [H, C.c_int64, C.c_int32, C.c_double, C.c_double]
+        L.orc_mp_update_xbar.argtypes = [H]
+        L.orc_mp_update_z.argtypes = [H, C.c_double]
+        L.orc_mp_update_l.argtypes = [H, C.c_double]
+        L.orc_mp_update_lz.argtypes = [H, C.c_double, C.c_double]
+        L.orc_mp_update_residual.argtypes = [H, _pd]
+        L.orc_mp_poststep.argtypes = [H, _pd]
+        L.orc_mp_poststep.restype = C.c_double
+        L.orc_mp_admm_two_level.argtypes = [H, C.POINTER(EaParams), C.POINTER(EaInfo), _pd]
+        L.orc_mp_admm_two_level.restype = C.c_int
         _lib = L
     return _lib
 
@@ -108,8 +135,22 @@ class OracleModel:
         self.inner = self.outer = self.cumul = 0
         self.res = np.zeros(4)
 
+    @classmethod
+    def borrowed(cls, handle, grid, params):
+        """View of a model owned by someone else (a period of ``OracleMpModel``): never destroyed here."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.grid, self.par = grid, params
+        self.h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+        self._borrowed = True
+        self.nvar = int(self.L.orc_nvar(self.h))
+        self.nline = grid.nline
+        self.inner = self.outer = self.cumul = 0
+        self.res = np.zeros(4)
+        return self
+
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and not getattr(self, "_borrowed", False):
             self.L.orc_destroy(self.h)
             self.h = None
 
@@ -208,3 +249,87 @@ def tron_solve(x0, xl, xu, param, Y, scale, max_feval=500, max_minor=200, gtol=1
     st = lib().orc_tron_solve(_p(x), _p(xl), _p(xu), _p(param), _p(Y), scale, max_feval, max_minor, gtol,
                               C.byref(minor), C.byref(nfev))
     return x, st, minor.value, nfev.value
+
+
+RAMP_FIELDS = {"u_curr": 0, "v_curr": 1, "l_curr": 2, "rho": 3, "rd": 4, "rp": 5, "z_outer": 6, "z_curr": 7,
+               "z_prev": 8, "lz": 9, "Ax_plus_By": 10, "s_curr": 11}
+
+
+class OracleMpModel:
+    """CPU-oracle twin of ``ModelMpacopf`` (src/models/mpacopf/) + its operator functions.
+
+    ``Pd``, ``Qd``: arrays (T, nbus) in MW / MVAr. ``models[t]`` are borrowed ``OracleModel`` views.
+    """
+
+    def __init__(self, grid, params, rho_pq: float, rho_va: float, Pd, Qd, ramp_ratio: float = 0.02):
+        self.L = lib()
+        self.grid, self.par = grid, params
+        Pd = np.ascontiguousarray(Pd, dtype=np.float64)
+        Qd = np.ascontiguousarray(Qd, dtype=np.float64)
+        assert Pd.ndim == 2 and Pd.shape == Qd.shape and Pd.shape[1] == grid.nbus
+        self.len_horizon = Pd.shape[0]
+        gs, self._keep = make_grid_struct(grid)
+        h = C.c_void_p()
+        rc = self.L.orc_mp_create(C.byref(gs), self.len_horizon, _p(Pd), _p(Qd), float(ramp_ratio), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"orc_mp_create failed: {rc}")
+        self.h = h
+        self.ngen = grid.ngen
+        self.nvar = int(self.L.orc_mp_nvar(h))
+        self.models = [OracleModel.borrowed(self.L.orc_mp_period(h, t), grid, params) for t in range(self.len_horizon)]
+        self.L.orc_mp_init_solution(h, rho_pq, rho_va)
+        self.inner = self.outer = self.cumul = 0
+        self.res = np.zeros(4)
+        self.err_ramp = 0.0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.models = []
+            self.L.orc_mp_destroy(self.h)
+            self.h = None
+
+    def set_threads(self, n): self.L.orc_mp_set_threads(self.h, int(n))
+
+    def ramp(self, t: int, name: str) -> np.ndarray:
+        ptr = self.L.orc_mp_ramp_vector(self.h, t, RAMP_FIELDS[name])
+        return np.ctypeslib.as_array(ptr, shape=(self.ngen,))
+
+    def gen_membuf(self, t: int) -> np.ndarray:
+        ptr = self.L.orc_mp_gen_membuf(self.h, t)
+        return np.ctypeslib.as_array(ptr, shape=(self.ngen, 8)).T
+
+    def init_solution(self, rho_pq, rho_va): self.L.orc_mp_init_solution(self.h, rho_pq, rho_va)
+    def admm_increment_outer(self): self.outer += 1
+    def admm_increment_reset_inner(self): self.inner = 0
+    def admm_increment_inner(self): self.inner += 1; self.cumul += 1
+    def admm_outer_prestep(self): self.norm_z_prev = self.L.orc_mp_outer_prestep(self.h)
+    def admm_inner_prestep(self): self.L.orc_mp_inner_prestep(self.h)
+
+    def admm_update_x(self):
+        self.L.orc_mp_update_x(self.h, self.inner, self.par.max_auglag, self.par.mu_max, self.par.scale)
+
+    def admm_update_xbar(self): self.L.orc_mp_update_xbar(self.h)
+    def admm_update_z(self): self.L.orc_mp_update_z(self.h, self.par.beta)
+    def admm_update_l(self): self.L.orc_mp_update_l(self.h, self.par.beta)
+    def admm_update_lz(self): self.L.orc_mp_update_lz(self.h, self.par.beta, self.par.MAX_MULTIPLIER)
+
+    def admm_update_residual(self):
+        self.L.orc_mp_update_residual(self.h, _p(self.res))
+        return self.res.copy()
+
+    def admm_poststep(self):
+        e = np.zeros(1)
+        obj = self.L.orc_mp_poststep(self.h, _p(e))
+        self.err_ramp = float(e[0])
+        return obj
+
+    def admm_two_level(self) -> EaInfo:
+        info = EaInfo()
+        ps = params_struct(self.par)
+        e = np.zeros(1)
+        rc = self.L.orc_mp_admm_two_level(self.h, C.byref(ps), C.byref(info), _p(e))
+        if rc != 0:
+            raise RuntimeError(f"orc_mp_admm_two_level failed: {rc}")
+        self.err_ramp = float(e[0])
+        self.par.beta = info.beta
+        return info
