@@ -11,9 +11,10 @@ from .environment import AdmmEnv, Parameters, IterationInformation, ComponentInf
 from .model import ModelAcopf, Solution  # noqa: E402
 from .solve_acopf import solve_acopf  # noqa: E402
 from .admm_two_level import admm_two_level, print_statistics  # noqa: E402
+from .mpacopf import ModelMpacopf, SolutionRamping, solve_mpacopf  # noqa: E402
 
 __all__ = ["AdmmEnv", "Parameters", "IterationInformation", "ComponentInformation", "ModelAcopf", "Solution",
-           "solve_acopf", "admm_two_level", "print_statistics", "OPFData", "parse_matpower", "parse_matpower_text", "write_matpower",
+           "solve_acopf", "solve_mpacopf", "ModelMpacopf", "SolutionRamping", "admm_two_level", "print_statistics", "OPFData", "parse_matpower", "parse_matpower_text", "write_matpower",
            "MatpowerFormatError", "GridData"]
 
 CASE9 = str(__import__("pathlib").Path(__file__).resolve().parent / "data" / "case9.m")

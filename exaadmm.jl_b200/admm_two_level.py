@@ -65,7 +65,11 @@ def _native(env, mod):
 def admm_two_level(env, mod, device=None, mode: str = "fused"):
     par, info = env.params, mod.info
     if mode == "native":
-        _native(env, mod)
+        if getattr(mod, "is_multiperiod", False):
+            from .mpacopf import admm_two_level_native
+            admm_two_level_native(env, mod)
+        else:
+            _native(env, mod)
         if par.verbose > 0:
             print_statistics(env, mod)
         return
@@ -93,7 +97,7 @@ def admm_two_level(env, mod, device=None, mode: str = "fused"):
         if stepwise:
             while info.inner < par.inner_iterlim:
                 ops.admm_increment_inner(env, mod, device)
-                if mode == "stepwise":
+                if mode == "stepwise" or getattr(mod, "is_multiperiod", False):
                     ops.admm_inner_prestep(env, mod, device)
                     ops.admm_update_x(env, mod, device)
                     ops.admm_update_xbar(env, mod, device)

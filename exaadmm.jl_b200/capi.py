@@ -108,6 +108,9 @@ _lib = None
 
 # name -> (restype, argtypes); must list every symbol include/exaadmm_b200.h declares
 _H = C.c_void_p
+RAMP_FIELDS = {"u_curr": 0, "v_curr": 1, "l_curr": 2, "rho": 3, "rd": 4, "rp": 5, "z_outer": 6, "z_curr": 7,
+               "z_prev": 8, "lz": 9, "Ax_plus_By": 10, "s_curr": 11}      # enum ea_ramp_field
+
 SIGNATURES = {
     "ea_abi_version": (C.c_int, []),
     "ea_last_error": (C.c_char_p, [_H]),
@@ -153,6 +156,31 @@ SIGNATURES = {
     "ea_reset_counters": (C.c_int, [_H]),
     "ea_set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
     "ea_get_kernel_times": (C.c_int, [_H, _pd]),
+    # multi-period model (ModelMpacopf)
+    "ea_mp_last_error": (C.c_char_p, [_H]),
+    "ea_mp_create": (C.c_int, [C.POINTER(EaGrid), C.c_int, C.c_int32, _pd, _pd, C.c_double, C.c_double, C.c_double,
+                               C.POINTER(_H)]),
+    "ea_mp_destroy": (None, [_H]),
+    "ea_mp_len_horizon": (C.c_int32, [_H]),
+    "ea_mp_nvar": (C.c_int64, [_H]),
+    "ea_mp_period": (_H, [_H, C.c_int32]),
+    "ea_mp_init_solution": (C.c_int, [_H, C.c_double, C.c_double]),
+    "ea_mp_get_ramp_vector": (C.c_int, [_H, C.c_int32, C.c_int, _pd, C.c_int64]),
+    "ea_mp_set_ramp_vector": (C.c_int, [_H, C.c_int32, C.c_int, _pd, C.c_int64]),
+    "ea_mp_get_gen_membuf": (C.c_int, [_H, C.c_int32, C.c_int, _pd, C.c_int64]),
+    "ea_mp_outer_prestep": (C.c_int, [_H, _pd]),
+    "ea_mp_inner_prestep": (C.c_int, [_H]),
+    "ea_mp_update_x": (C.c_int, [_H, C.c_int64, C.c_int32, C.c_double, C.c_double]),
+    "ea_mp_update_xbar": (C.c_int, [_H]),
+    "ea_mp_update_z": (C.c_int, [_H, C.c_double]),
+    "ea_mp_update_l": (C.c_int, [_H, C.c_double]),
+    "ea_mp_update_lz": (C.c_int, [_H, C.c_double, C.c_double]),
+    "ea_mp_update_residual": (C.c_int, [_H, _pd]),
+    "ea_mp_poststep": (C.c_int, [_H, _pd, _pd]),
+    "ea_mp_run_inner": (C.c_int, [_H, C.c_int64, C.c_double, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int32,
+                                  C.POINTER(C.c_int64), _pd]),
+    "ea_mp_admm_two_level": (C.c_int, [_H, C.POINTER(EaParams), C.POINTER(EaInfo), _pd]),
+    "ea_mp_get_kernel_times": (C.c_int, [_H, _pd]),
     "ea_diag_fp64_peak": (C.c_int, [C.c_int, _pd]),
     "ea_diag_branch_eval": (C.c_int, [C.c_int, C.c_int64, _pd, _pd, _pd, C.c_double, _pd, _pd, _pd]),
 }

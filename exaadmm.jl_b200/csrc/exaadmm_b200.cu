@@ -3,6 +3,7 @@
 // admm_two_level driver. No torch, no CPU fallback.
 #include "../../include/exaadmm_b200.h"
 #include "kernels.cuh"
+#include "mp_kernels.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -110,7 +111,7 @@ const char *load_nccl(const char *path) {
 
 namespace {
 
-int fail(ea_handle *h, int code, const char *fmt, ...) {
+template <typename H> int fail(H *h, int code, const char *fmt, ...) {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
     if (h) h->err = buf; else g_create_error = buf;
@@ -127,7 +128,7 @@ int fail(ea_handle *h, int code, const char *fmt, ...) {
 // Device memory comes from the stream-ordered pool (cudaMallocAsync) with an unlimited release threshold: handles
 // are created and destroyed per solve by drop-in callers (solve_acopf builds a model per call), and the pool turns the
 // ~50 allocations of ea_create into pointer bumps after the first handle.
-template <typename T> int dev_alloc(ea_handle *h, T **p, size_t n) {
+template <typename H, typename T> int dev_alloc(H *h, T **p, size_t n) {
     void *q = nullptr;
     CK(cudaMallocAsync(&q, std::max<size_t>(n, 1) * sizeof(T), h->stream));
     CK(cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
@@ -135,7 +136,7 @@ template <typename T> int dev_alloc(ea_handle *h, T **p, size_t n) {
     *p = static_cast<T *>(q);
     return EA_OK;
 }
-template <typename T> int dev_upload(ea_handle *h, T **p, const std::vector<T> &v) {
+template <typename H, typename T> int dev_upload(H *h, T **p, const std::vector<T> &v) {
     int rc = dev_alloc(h, p, v.size());
     if (rc) return rc;
     if (!v.empty()) CK(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
@@ -173,14 +174,16 @@ int sync_ctrl_to_device(ea_handle *h, double beta, double eps_pri, long long inn
     return EA_OK;
 }
 
-int launch_x(ea_handle *h, long long major, int zsel, int max_auglag, double mu_max, double scale, int lines, int gens) {
+int launch_x(ea_handle *h, long long major, int zsel, int max_auglag, double mu_max, double scale, int lines, int gens,
+             cudaStream_t stream = nullptr) {
+    if (!stream) stream = h->stream;
     build_pow_table(h, mu_max);
     if (major > 0 && lines)     // step-wise call: the fused loop resets the work queue itself (k_bus / k_ctrl_begin)
-        CK(cudaMemsetAsync(&h->d.ctrl->next_line, 0, sizeof(int), h->stream));
+        CK(cudaMemsetAsync(&h->d.ctrl->next_line, 0, sizeof(int), stream));
     // persistent grid: as many CTAs as are resident at once, capped by the work available
     const int64_t work_blocks = std::max<int64_t>((h->nline + XBLOCK - 1) / XBLOCK, (h->ngen + XBLOCK - 1) / XBLOCK);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->x_resident_blocks, work_blocks));
-    k_xupdate<<<grid, XBLOCK, XTILE_BYTES, h->stream>>>(h->d, h->pow_table, major, zsel, max_auglag, mu_max, scale, lines, gens);
+    k_xupdate<<<grid, XBLOCK, XTILE_BYTES, stream>>>(h->d, h->pow_table, major, zsel, max_auglag, mu_max, scale, lines, gens);
     CK(cudaGetLastError());
     h->n_x++;
     return EA_OK;
@@ -1097,3 +1100,5 @@ int ea_diag_fp64_peak(int device, double *tflops) {
 }
 
 }  // extern "C"
+
+#include "mp_host.inc"

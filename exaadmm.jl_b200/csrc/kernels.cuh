@@ -73,6 +73,12 @@ struct Dev {                  // everything the kernels need, passed by value
     int peer_mode;
     double *xbase;                        // this rank's exchange buffer
     double *const *peer_base;             // device array: every rank's buffer as mapped into this process
+    // multi-period model (mp_kernels.cuh): this handle is period t of T. The consensus value of pg also serves the
+    // NEXT period's copy phat_t, so the bus kernel needs that period's ramp vectors (generator slot order; null for
+    // the last period and for single-period handles). mp_sums: the fused bus kernel hands its four sums of squares
+    // over instead of finishing the iteration itself (k_mp_finish does, for all periods at once).
+    const double *rn_u, *rn_l, *rn_rho, *rn_z[2];
+    double *mp_sums;
 };
 
 __device__ __forceinline__ double *xseg(const Dev &d, double *base, int parity, int r) {
@@ -85,7 +91,6 @@ __device__ __forceinline__ unsigned long long *xflag(const Dev &d, double *base,
 // ---------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------
-struct __align__(16) d2 { double x, y; };
 struct __align__(32) d4 { double p, q, w, t; };
 
 __device__ __forceinline__ d4 ld4(const double *base, int slot) {
@@ -396,17 +401,25 @@ constexpr int BBLOCK = 128;
 struct BusSolve { double mu1, mu2, wi, ti; };
 
 // gather side of one generator of the bus (acopf_bus_kernel_gpu.jl:45-63)
-__device__ __forceinline__ void bus_gen_gather(const Dev &d, const double *zold, int k, double &rhs1, double &rhs2,
-                                               double &inv_pg, double &inv_qg) {
+__device__ __forceinline__ void bus_gen_gather(const Dev &d, const double *zold, int zsel, int k, double &rhs1,
+                                               double &rhs2, double &inv_pg, double &inv_qg) {
     const double2 u = *reinterpret_cast<const double2 *>(d.u + 2 * k);
     const double2 z = *reinterpret_cast<const double2 *>(zold + 2 * k);
     const double2 l = *reinterpret_cast<const double2 *>(d.l + 2 * k);
     const double2 r = *reinterpret_cast<const double2 *>(d.rho + 2 * k);
-    const double ix = tron::ddiv(1.0, r.x), iy = tron::ddiv(1.0, r.y);
-    rhs1 += (u.x + z.x) + (l.x * ix);
+    const double iy = tron::ddiv(1.0, r.y);
     rhs2 += (u.y + z.y) + (l.y * iy);
-    inv_pg += ix;
     inv_qg += iy;
+    if (d.rn_u) {                          // ramp-coupled generator (mpacopf_bus_kernel_gpu.jl:47-60)
+        const double rr = d.rn_rho[k];
+        const double ix = tron::ddiv(1.0, r.x + rr);
+        rhs1 += ((l.x + r.x * (u.x + z.x)) + (d.rn_l[k] + rr * (d.rn_u[k] + d.rn_z[zsel][k]))) * ix;
+        inv_pg += ix;
+    } else {
+        const double ix = tron::ddiv(1.0, r.x);
+        rhs1 += (u.x + z.x) + (l.x * ix);
+        inv_pg += ix;
+    }
 }
 
 // the 2x2 solve of the bus (acopf_bus_kernel_gpu.jl:83-94)
@@ -432,14 +445,18 @@ __device__ __forceinline__ BusSolve bus_solve(const Dev &d, int b, double common
 }
 
 template <bool FUSED>
-__device__ __forceinline__ void bus_gen_scatter(const Dev &d, const double *zold, double *znew, int k, const BusSolve &bs,
-                                                double beta, double (&acc)[4]) {
+__device__ __forceinline__ void bus_gen_scatter(const Dev &d, const double *zold, double *znew, int zsel, int k,
+                                                const BusSolve &bs, double beta, double (&acc)[4]) {
     const double2 u = *reinterpret_cast<const double2 *>(d.u + 2 * k);
     const double2 z = *reinterpret_cast<const double2 *>(zold + 2 * k);
     const double2 l = *reinterpret_cast<const double2 *>(d.l + 2 * k);
     const double2 r = *reinterpret_cast<const double2 *>(d.rho + 2 * k);
     double2 v;
-    v.x = (u.x + z.x) + (l.x - bs.mu1) * tron::ddiv(1.0, r.x);
+    if (d.rn_u) {                          // mpacopf_bus_kernel_gpu.jl:100-103
+        const double rr = d.rn_rho[k];
+        v.x = ((l.x + r.x * (u.x + z.x)) + (d.rn_l[k] + rr * (d.rn_u[k] + d.rn_z[zsel][k])) - bs.mu1) * tron::ddiv(1.0, r.x + rr);
+    } else
+        v.x = (u.x + z.x) + (l.x - bs.mu1) * tron::ddiv(1.0, r.x);
     v.y = (u.y + z.y) + (l.y - bs.mu2) * tron::ddiv(1.0, r.y);
     *reinterpret_cast<double2 *>(d.v + 2 * k) = v;
     if (FUSED) {
@@ -503,12 +520,13 @@ __device__ __forceinline__ void bus_end_scatter(const Dev &d, double *znew, int 
 
 // one whole bus on one lane (buses with > 32 ends or none)
 template <bool FUSED>
-__device__ __forceinline__ void bus_scalar(const Dev &d, const double *zold, double *znew, int b, double beta, double (&acc)[4]) {
+__device__ __forceinline__ void bus_scalar(const Dev &d, const double *zold, double *znew, int zsel, int b, double beta,
+                                           double (&acc)[4]) {
     const int hs = d.hstart[b], he = d.hstart[b + 1], gs = d.gstart[b], ge = d.gstart[b + 1];
     const double *uh = d.u + d.gpad, *zh = zold + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
     double common_wi = 0.0, common_ti = 0.0, inv_p = 0.0, inv_q = 0.0, rs_w = 0.0, rs_t = 0.0;
     double rhs1 = 0.0, rhs2 = 0.0, inv_pg = 0.0, inv_qg = 0.0;
-    for (int k = gs; k < ge; ++k) bus_gen_gather(d, zold, k, rhs1, rhs2, inv_pg, inv_qg);
+    for (int k = gs; k < ge; ++k) bus_gen_gather(d, zold, zsel, k, rhs1, rhs2, inv_pg, inv_qg);
     rhs1 -= d.pd_pu[b];
     rhs2 -= d.qd_pu[b];
     for (int s = hs; s < he; ++s) {
@@ -524,7 +542,7 @@ __device__ __forceinline__ void bus_scalar(const Dev &d, const double *zold, dou
         rhs2 -= (u.q + z.q) + (l.q * irq);
     }
     const BusSolve bs = bus_solve(d, b, common_wi, common_ti, inv_p, inv_q, rs_w, rs_t, rhs1, rhs2, inv_pg, inv_qg);
-    for (int k = gs; k < ge; ++k) bus_gen_scatter<FUSED>(d, zold, znew, k, bs, beta, acc);
+    for (int k = gs; k < ge; ++k) bus_gen_scatter<FUSED>(d, zold, znew, zsel, k, bs, beta, acc);
     for (int s = hs; s < he; ++s) {
         const d4 u = ld4(uh, s), z = ld4(zh, s), l = ld4(lh, s), r = ld4(rh, s);
         bus_end_scatter<FUSED>(d, znew, s, u, z, l, r, tron::ddiv(1.0, r.p), tron::ddiv(1.0, r.q), bs, beta, acc);
@@ -551,7 +569,7 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
         const int4 info = d.lane_info[(size_t)gw * 32 + lane];      // one coalesced load, no dependent index chain
         const int s = info.x, b = info.y, L = info.w;
         if (__shfl_sync(full, L, 0) < 0) {                           // a bus with > 32 ends (or none): scalar path
-            if (lane == 0) bus_scalar<FUSED>(d, zold, znew, b, beta, acc);
+            if (lane == 0) bus_scalar<FUSED>(d, zold, znew, zsel, b, beta, acc);
         } else {
             const bool active = s >= 0;
             const bool leader = L > 0;
@@ -568,7 +586,7 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
             int gs = 0, ge = 0;
             if (leader) {
                 gs = d.gstart[b]; ge = d.gstart[b + 1];
-                for (int k = gs; k < ge; ++k) bus_gen_gather(d, zold, k, rhs1, rhs2, inv_pg, inv_qg);
+                for (int k = gs; k < ge; ++k) bus_gen_gather(d, zold, zsel, k, rhs1, rhs2, inv_pg, inv_qg);
                 rhs1 -= d.pd_pu[b];
                 rhs2 -= d.qd_pu[b];
             }
@@ -589,7 +607,7 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
             bs.mu1 = __shfl_sync(full, bs.mu1, src); bs.mu2 = __shfl_sync(full, bs.mu2, src);
             bs.wi = __shfl_sync(full, bs.wi, src);   bs.ti = __shfl_sync(full, bs.ti, src);
             if (leader)
-                for (int k = gs; k < ge; ++k) bus_gen_scatter<FUSED>(d, zold, znew, k, bs, beta, acc);
+                for (int k = gs; k < ge; ++k) bus_gen_scatter<FUSED>(d, zold, znew, zsel, k, bs, beta, acc);
             if (active) bus_end_scatter<FUSED>(d, znew, s, u, z, l, r, t_ip, t_iq, bs, beta, acc);
         }
     }
@@ -615,6 +633,10 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
                 unsigned long long *f = xflag(d, d.peer_base[threadIdx.x], par, d.rank);
                 asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(seq + 1ull) : "memory");
             }
+        } else if (last && threadIdx.x == 0 && d.mp_sums) {
+            // a period of a multi-period model: k_mp_finish combines the periods and runs the termination test
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d.mp_sums[k] = acc[k];
         } else if (last && threadIdx.x == 0 && d.partitioned) {
             // partial sums over this rank's entries; norms and the termination test follow the all-gather (k_finish)
 #pragma unroll

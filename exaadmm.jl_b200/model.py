@@ -93,6 +93,31 @@ class ModelAcopf:
         self._check(self.lib.ea_init_solution(self.h, env.initial_rho_pq, env.initial_rho_va))   # :83
         self.info = IterationInformation()
 
+    @classmethod
+    def borrowed(cls, env: AdmmEnv, handle, grid: GridData, ramp_ratio: float = 0.02) -> "ModelAcopf":
+        """A period of a multi-period model: the handle is owned by the ``ModelMpacopf`` (``ea_mp_period``) and has
+        been initialised by it; nothing is created or destroyed here."""
+        self = cls.__new__(cls)
+        self.lib = capi.load_library()
+        self.env = env
+        self.grid_data = g = grid
+        self.n = 6
+        self.nline_padded = g.nline
+        self.nvar = self.nvar_padded = self.nvar_u = self.nvar_u_padded = 2 * g.ngen + 8 * g.nline
+        self.gen_start = 1
+        self.line_start = 2 * g.ngen + 1
+        self.pgmin_curr = g.pgmin.copy()
+        self.pgmax_curr = g.pgmax.copy()
+        g.ramp_rate = ramp_ratio * g.pgmax
+        self.nvar_v = 2 * g.ngen + 4 * g.nline + 2 * g.nbus
+        self.bus_start = 2 * g.ngen + 4 * g.nline + 1
+        self.h = handle
+        self._borrowed = True
+        self.solution = Solution(self)
+        self.gen_solution = None
+        self.info = IterationInformation()
+        return self
+
     # -- plumbing ---------------------------------------------------------------
     def _check(self, rc: int):
         if rc != 0:
@@ -100,7 +125,8 @@ class ModelAcopf:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.ea_destroy(self.h)
+            if not getattr(self, "_borrowed", False):
+                self.lib.ea_destroy(self.h)
             self.h = None
 
     def __del__(self):

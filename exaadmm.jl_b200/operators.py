@@ -15,28 +15,47 @@ import numpy as np
 from .capi import dptr
 
 
+def _mp(mod):
+    """Dispatch on the model type, as the reference's multiple dispatch does: ``ModelMpacopf`` has its own methods
+    (src/models/mpacopf/), implemented in mpacopf.py."""
+    if getattr(mod, "is_multiperiod", False):
+        from . import mpacopf
+        return mpacopf
+    return None
+
+
 # -- counters: acopf_admm_increment.jl:1-36 ------------------------------------
 def admm_increment_outer(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_increment_outer(env, mod)
     mod.info.outer += 1
 
 
 def admm_increment_reset_inner(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_increment_reset_inner(env, mod)
     mod.info.inner = 0
 
 
 def admm_increment_inner(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_increment_inner(env, mod)
     mod.info.inner += 1
     mod.info.cumul += 1
 
 
 # -- pre/post steps: acopf_admm_prepoststep_gpu.jl -------------------------------
 def admm_outer_prestep(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_outer_prestep(env, mod)
     out = C.c_double()
     mod._check(mod.lib.ea_outer_prestep(mod.h, C.byref(out)))
     mod.info.norm_z_prev = out.value
 
 
 def admm_inner_prestep(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_inner_prestep(env, mod)
     mod._check(mod.lib.ea_inner_prestep(mod.h))
 
 
@@ -45,6 +64,8 @@ def admm_poststep(env, mod, device=None):
         # the reference calls pf_projection, which is commented out of the module
         # (ExaAdmm.jl:127-134) -> UndefVarError there; refuse explicitly here.
         raise NotImplementedError("use_projection=true is not available on this path (SURVEY.md §2)")
+    if _mp(mod):
+        return _mp(mod).admm_poststep(env, mod)
     out = C.c_double()
     mod._check(mod.lib.ea_poststep(mod.h, C.byref(out)))
     mod.info.objval = out.value
@@ -61,27 +82,39 @@ def acopf_admm_update_x_line(env, mod):
 
 
 def admm_update_x(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_update_x(env, mod)
     acopf_admm_update_x_gen(env, mod, mod.gen_solution)
     acopf_admm_update_x_line(env, mod)
 
 
 def admm_update_xbar(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_update_xbar(env, mod)
     mod._check(mod.lib.ea_update_xbar(mod.h))
 
 
 def admm_update_z(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_update_z(env, mod)
     mod._check(mod.lib.ea_update_z(mod.h, env.params.beta))
 
 
 def admm_update_l(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_update_l(env, mod)
     mod._check(mod.lib.ea_update_l(mod.h, env.params.beta))
 
 
 def admm_update_lz(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_update_lz(env, mod)
     mod._check(mod.lib.ea_update_lz(mod.h, env.params.beta, env.params.MAX_MULTIPLIER))
 
 
 def admm_update_residual(env, mod, device=None):
+    if _mp(mod):
+        return _mp(mod).admm_update_residual(env, mod)
     out = np.zeros(4)
     mod._check(mod.lib.ea_update_residual(mod.h, dptr(out)))
     info = mod.info
@@ -102,6 +135,8 @@ def admm_inner_iteration(env, mod, device=None):
 
 def admm_run_inner(env, mod, chunk: int = 0):
     """The whole inner ``while`` of one outer iteration on the device."""
+    if _mp(mod):
+        return _mp(mod).admm_run_inner(env, mod, chunk)
     par = env.params
     out = np.zeros(4)
     done = C.c_int64()

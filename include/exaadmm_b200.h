@@ -267,6 +267,53 @@ int  ea_part_get_message(ea_handle_t *h, double *host, int64_t n);
 int  ea_part_put_gathered(ea_handle_t *h, const double *host, int64_t n);
 int  ea_part_end(ea_handle_t *h, double out[4]);
 
+/* ---- multi-period ACOPF: `ModelMpacopf` (src/models/mpacopf/) --------
+ * T copies of the single-period model on one device, period t = 0..T-1 with its own loads, coupled
+ * through the generator ramp constraints |pg_t - pg_{t-1}| <= ramp_rate. The periods are ordinary
+ * handles (ea_mp_period; borrowed, do not destroy) so every single-period accessor works on them
+ * (`mod.models[i].solution`, membuf, ...); the ramp vectors (`mod.solution[i]`, SolutionRamping)
+ * are read with ea_mp_get_ramp_vector. One host thread per model, as in the reference. */
+typedef struct ea_mp_handle ea_mp_handle_t;
+const char *ea_mp_last_error(const ea_mp_handle_t *h);   /* h may be NULL: last ea_mp_create error */
+/* ModelMpacopf constructor (mpacopf_model.jl:56-109) + init_solution!. Pd, Qd: T x nbus (period-major),
+ * MW / MVAr; ramp_rate = ramp_ratio * pgmax (acopf_model.jl:66-67). */
+int  ea_mp_create(const ea_grid_t *grid, int device, int32_t T, const double *Pd, const double *Qd,
+                  double ramp_ratio, double rho_pq, double rho_va, ea_mp_handle_t **out);
+void ea_mp_destroy(ea_mp_handle_t *h);
+int32_t ea_mp_len_horizon(const ea_mp_handle_t *h);
+int64_t ea_mp_nvar(const ea_mp_handle_t *h);              /* mod.nvar: nvar + ngen (T > 1), mpacopf_model.jl:97-102 */
+ea_handle_t *ea_mp_period(ea_mp_handle_t *h, int32_t t); /* mod.models[t+1] */
+/* init_solution!(mod::ModelMpacopf, ...) (mpacopf_init_solution_gpu.jl:16-35); gen_membuf persists. */
+int  ea_mp_init_solution(ea_mp_handle_t *h, double rho_pq, double rho_va);
+/* mod.solution[t+1].<field> (enum ea_ramp_field), n = ngen, reference generator order; t >= 1. */
+int  ea_mp_get_ramp_vector(ea_mp_handle_t *h, int32_t t, int field, double *host, int64_t n);
+int  ea_mp_set_ramp_vector(ea_mp_handle_t *h, int32_t t, int field, const double *host, int64_t n);
+/* gen_membuf rows 7 (multiplier of the ramp equality) and 8 (its penalty xi) of period t >= 1. */
+int  ea_mp_get_gen_membuf(ea_mp_handle_t *h, int32_t t, int row, double *host, int64_t n);
+/* The operators of the generic loop for mod::ModelMpacopf, file by file:
+ * mpacopf_admm_prepoststep_gpu.jl:1-38 (outer / inner prestep), mpacopf_admm_update_x_gpu.jl:1-46
+ * (generators of period 1 closed form, periods >= 2 AL + TRON with n = 3, then every period's
+ * branches), mpacopf_admm_update_xbar_gpu.jl + mpacopf_bus_kernel_gpu.jl (ramp-aware bus update),
+ * mpacopf_admm_update_{z,l,lz,residual}_gpu.jl, mpacopf_admm_prepoststep_gpu.jl:40-78 (poststep:
+ * objval = sum over periods, err_ramp = largest ramp violation). */
+int  ea_mp_outer_prestep(ea_mp_handle_t *h, double *norm_z_prev);
+int  ea_mp_inner_prestep(ea_mp_handle_t *h);
+int  ea_mp_update_x(ea_mp_handle_t *h, int64_t inner, int32_t max_auglag, double mu_max, double scale);
+int  ea_mp_update_xbar(ea_mp_handle_t *h);
+int  ea_mp_update_z(ea_mp_handle_t *h, double beta);
+int  ea_mp_update_l(ea_mp_handle_t *h, double beta);
+int  ea_mp_update_lz(ea_mp_handle_t *h, double beta, double max_multiplier);
+int  ea_mp_update_residual(ea_mp_handle_t *h, double out[4]);
+int  ea_mp_poststep(ea_mp_handle_t *h, double *objval, double *err_ramp);
+/* Fused forms (all periods advance together, termination test on the device):
+ * the inner `while` of one outer iteration, and admm_two_level end to end. */
+int  ea_mp_run_inner(ea_mp_handle_t *h, int64_t outer, double beta, int64_t inner_iterlim, int32_t max_auglag,
+                     double mu_max, double scale, int32_t chunk, int64_t *inner_done, double out[4]);
+int  ea_mp_admm_two_level(ea_mp_handle_t *h, const ea_params_t *par, ea_info_t *info, double *err_ramp);
+/* Launch accounting of the fused loop: out = { device seconds in ea_mp_run_inner, kernels launched,
+ * inner iterations executed, 0 }. */
+int  ea_mp_get_kernel_times(ea_mp_handle_t *h, double out[4]);
+
 int  ea_get_counters(ea_handle_t *h, ea_counters_t *out);
 int  ea_reset_counters(ea_handle_t *h);
 /* Options: "count_work" (0/1, atomics for ea_counters_t in the branch kernel, default 1),

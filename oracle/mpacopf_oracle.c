@@ -161,6 +161,38 @@ static void gen_gh(const double *x, const void *c, double *g, double *A) {
         for (int j = 0; j <= i; ++j) { A[i * NV + j] = H[i][j]; A[j * NV + i] = H[i][j]; }
 }
 
+/* The AL loop around TRON for ONE generator (mpacopf_auglag_generator_kernel_cpu.jl:66-127).
+ * param: gen_membuf column (8 doubles, rows 1-6 set by the caller, [6] = multiplier, [7] = xi; both
+ * updated in place). work (optional): {auglag iterations, f-evaluations, cg iterations}. */
+void orc_gen_ramp_solve(double x[3], const double xl[3], const double xu[3], double *param, double c2, double c1,
+                        double c0, double baseMVA, double scale, int32_t max_auglag, double xi_max, int32_t *work) {
+    const gen_ctx_t ctx = { param, scale, c2, c1, c0, baseMVA };
+    double xi = param[7];
+    double eta = 1 / pow(xi, 0.1);
+    int it = 0, terminate = 0;
+    tron_stats_t st; memset(&st, 0, sizeof(st));
+    while (!terminate) {
+        it++;
+        int minor;
+        orc__tron_cb(3, x, xl, xu, gen_f, gen_gh, &ctx, 500, 200, 1e-6, &minor, &st);
+        const double cviol = x[0] - x[1] - x[2];
+        const double cnorm = fabs(cviol);
+        if (cnorm <= eta) {
+            if (cnorm <= 1e-6) terminate = 1;
+            else {
+                param[6] += xi * cviol;
+                eta = eta / pow(xi, 0.9);
+            }
+        } else {
+            xi = mp_dmin(xi_max, xi * 10);
+            eta = 1 / pow(xi, 0.1);
+            param[7] = xi;
+        }
+        if (it >= max_auglag) terminate = 1;
+    }
+    if (work) { work[0] = it; work[1] = (int32_t)st.nfev; work[2] = (int32_t)st.cg; }
+}
+
 /* mpacopf_auglag_generator_kernel_cpu.jl:1-129 — generators of period t >= 1 */
 static void gen_ramp_update(orc_mp_t *mp, int t, int64_t major_iter, int32_t max_auglag, double xi_max, double scale) {
     orc_model_t *m = mp->m[t];
@@ -188,31 +220,8 @@ static void gen_ramp_update(orc_mp_t *mp, int t, int64_t major_iter, int32_t max
         param[3] = r_rho[I];
         param[4] = v[pg] - z[pg];
         param[5] = r_v[pg] - r_z[I];
-        double xi;
-        if (major_iter <= 1) { param[7] = 10.0; xi = 10.0; } else xi = param[7];
-        const gen_ctx_t ctx = { param, scale, m->c2[I], m->c1[I], m->c0[I], m->baseMVA };
-        double eta = 1 / pow(xi, 0.1);
-        int it = 0, terminate = 0;
-        tron_stats_t st; memset(&st, 0, sizeof(st));
-        while (!terminate) {
-            it++;
-            int minor;
-            orc__tron_cb(3, x, xl, xu, gen_f, gen_gh, &ctx, 500, 200, 1e-6, &minor, &st);
-            const double cviol = x[0] - x[1] - x[2];
-            const double cnorm = fabs(cviol);
-            if (cnorm <= eta) {
-                if (cnorm <= 1e-6) terminate = 1;
-                else {
-                    param[6] += xi * cviol;
-                    eta = eta / pow(xi, 0.9);
-                }
-            } else {
-                xi = mp_dmin(xi_max, xi * 10);
-                eta = 1 / pow(xi, 0.1);
-                param[7] = xi;
-            }
-            if (it >= max_auglag) terminate = 1;
-        }
+        if (major_iter <= 1) param[7] = 10.0;
+        orc_gen_ramp_solve(x, xl, xu, param, m->c2[I], m->c1[I], m->c0[I], m->baseMVA, scale, max_auglag, xi_max, NULL);
         u[pg] = x[0];
         r_u[I] = x[1];
         r_s[I] = x[2];

@@ -46,6 +46,10 @@ void   orc_mp_update_residual(orc_mp_t *mp, double out[4]);
 double orc_mp_poststep(orc_mp_t *mp, double *err_ramp);
 int    orc_mp_admm_two_level(orc_mp_t *mp, const ea_params_t *par, ea_info_t *info, double *err_ramp);
 
+/* unit level: one generator's AL + TRON solve (see mpacopf_oracle.c) */
+void   orc_gen_ramp_solve(double x[3], const double xl[3], const double xu[3], double *param, double c2, double c1,
+                          double c0, double baseMVA, double scale, int32_t max_auglag, double xi_max, int32_t *work);
+
 #ifdef __cplusplus
 }
 #endif

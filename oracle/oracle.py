@@ -108,6 +108,8 @@ def lib():
         L.orc_mp_poststep.restype = C.c_double
         L.orc_mp_admm_two_level.argtypes = [H, C.POINTER(EaParams), C.POINTER(EaInfo), _pd]
         L.orc_mp_admm_two_level.restype = C.c_int
+        L.orc_gen_ramp_solve.argtypes = [_pd, _pd, _pd, _pd, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         C.c_int32, C.c_double, C.POINTER(C.c_int32)]
         _lib = L
     return _lib
 

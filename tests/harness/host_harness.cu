@@ -3,6 +3,7 @@
 // suite can drive exactly the code the GPU runs (flattened AL/TRON loop, masked
 // free-set) against the oracle without a GPU. Not part of the product library.
 #include "../../exaadmm.jl_b200/csrc/branch.cuh"
+#include "../../exaadmm.jl_b200/csrc/genramp.cuh"
 #include <cmath>
 #include <cstring>
 
@@ -83,6 +84,22 @@ void hh_eval(const double *x, const double *param, const double *Y, double scale
     branch::Sym6 A;
     branch::eval_fgh(branch::StructView{ &D }, ls, param[26], scale, xx, *f, gg, A, F);
     for (int a = 0; a < 6; ++a) { g[a] = gg[a]; for (int b = 0; b < 6; ++b) H[6 * a + b] = A.a[tron::tri(a, b)]; }
+}
+
+// One generator of the multi-period model (genramp.cuh). param: gen_membuf column (8 doubles; [6] multiplier and
+// [7] xi updated in place). work[3]: auglag iterations, f-evaluations, cg iterations.
+void hh_solve_gen(double *x, const double *xl, const double *xu, double *param, double c2, double c1, double c0,
+                  double baseMVA, double scale, int max_auglag, double xi_max, int *work) {
+    branch::PowTable T;
+    make_pow_table(T, xi_max);
+    const genramp::Problem P = { param[0], param[1], param[2], param[3], param[4], param[5], c2, c1, c0, baseMVA, scale };
+    double xx[3] = { x[0], x[1], x[2] }, l[3] = { xl[0], xl[1], xl[2] }, u[3] = { xu[0], xu[1], xu[2] };
+    double mu = param[6], xi = param[7];
+    int evals = 0, cg = 0, it = 0;
+    genramp::solve(P, mu, xi, xx, l, u, max_auglag, xi_max, T, evals, cg, it);
+    for (int k = 0; k < 3; ++k) x[k] = xx[k];
+    param[6] = mu; param[7] = xi;
+    work[0] = it; work[1] = evals; work[2] = cg;
 }
 
 }

@@ -134,3 +134,57 @@ def test_branch_solver_random_problems_fma_build(host_harness):
         total += 1
         same_path += (work[1] == nfev) and np.allclose(xc, xo, rtol=0, atol=1e-10)
     assert same_path >= 0.95 * total, (same_path, total)
+
+
+# ---------------------------------------------------------------------------
+# multi-period model: the n = 3 generator sub-problem (genramp.cuh) against the oracle
+# ---------------------------------------------------------------------------
+def _gen_problems(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        pmax = rng.uniform(0.5, 4.0)
+        pmin = rng.uniform(0.0, 0.4) * pmax
+        ramp = rng.choice([0.02, 0.1, 0.5]) * pmax
+        xl = np.array([pmin, pmin, -ramp]); xu = np.array([pmax, pmax, ramp])
+        x0 = np.array([rng.uniform(pmin, pmax), rng.uniform(pmin, pmax), rng.uniform(-ramp, ramp)])
+        rho = rng.choice([10.0, 400.0, 3e4])
+        param = np.array([rng.normal() * 50, rng.normal() * 50, rho, rho, rng.uniform(pmin, pmax) + rng.normal() * 0.05,
+                          rng.uniform(pmin, pmax) + rng.normal() * 0.05, rng.normal() * 5.0, rng.choice([10.0, 100.0, 1e4])])
+        cost = (rng.uniform(0.01, 0.2), rng.uniform(5, 40), rng.uniform(0, 500))
+        out.append((x0, xl, xu, param, cost))
+    return out
+
+
+def _run_gen(fn, x0, xl, xu, param, cost, max_auglag=50, xi_max=1e8, i32=False):
+    import ctypes as C
+    x, p = x0.copy(), param.copy()
+    work = (C.c_int32 * 3)() if i32 else (C.c_int * 3)()
+    pd = C.POINTER(C.c_double)
+    fn(x.ctypes.data_as(pd), xl.ctypes.data_as(pd), xu.ctypes.data_as(pd), p.ctypes.data_as(pd), cost[0], cost[1], cost[2],
+       100.0, 1.0, max_auglag, xi_max, work)
+    return x, p, list(work)
+
+
+def test_generator_ramp_solve_bit_exact_logic(host_harness_nofma):
+    """-DEA_NO_FMA build: same arithmetic as the oracle => identical iterates and counts."""
+    from oracle.oracle import lib
+    L = lib()
+    for prob in _gen_problems(300, 11):
+        xo, po, wo = _run_gen(L.orc_gen_ramp_solve, *prob, i32=True)
+        xh, ph, wh = _run_gen(host_harness_nofma.hh_solve_gen, *prob)
+        assert wo == wh, (wo, wh)
+        np.testing.assert_array_equal(xo, xh)
+        np.testing.assert_array_equal(po, ph)
+
+
+def test_generator_ramp_solve_fma_build_close(host_harness):
+    from oracle.oracle import lib
+    L = lib()
+    for prob in _gen_problems(300, 12):
+        xo, po, wo = _run_gen(L.orc_gen_ramp_solve, *prob, i32=True)
+        xh, ph, wh = _run_gen(host_harness.hh_solve_gen, *prob)
+        np.testing.assert_allclose(xh, xo, atol=1e-9, rtol=0)
+        np.testing.assert_allclose(ph[6:], po[6:], atol=1e-6, rtol=1e-9)
+        # the ramp equality holds to the AL tolerance
+        assert abs(xh[0] - xh[1] - xh[2]) <= 1e-6 or wh[0] == 50
