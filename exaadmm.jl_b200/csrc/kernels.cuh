@@ -550,9 +550,7 @@ __device__ __forceinline__ void bus_scalar(const Dev &d, const double *zold, dou
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(BBLOCK, 5)
-k_bus(Dev d, int zsel_arg, double beta_arg) {
-    __shared__ double red[4 * (BBLOCK / 32)];
+__device__ __forceinline__ void bus_body(const Dev &d, int zsel_arg, double beta_arg, double *red) {
     int zsel = zsel_arg;
     double beta = beta_arg;
     if (FUSED && zsel_arg < 0) {
@@ -653,6 +651,23 @@ k_bus(Dev d, int zsel_arg, double beta_arg) {
             if (c->res[0] <= c->eps_pri || inner >= c->inner_limit) c->done = 1;
         }
     }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(BBLOCK, 5)
+k_bus(Dev d, int zsel_arg, double beta_arg) {
+    __shared__ double red[4 * (BBLOCK / 32)];
+    bus_body<FUSED>(d, zsel_arg, beta_arg, red);
+}
+
+// All periods of a multi-period model in one launch: blockIdx.y = period, every period has its own
+// partial-sum buffer and ticket (mp_kernels.cuh).
+template <bool FUSED>
+__global__ void __launch_bounds__(BBLOCK, 5)
+k_bus_mp(const Dev *devs, int zsel_arg, double beta_arg) {
+    __shared__ double red[4 * (BBLOCK / 32)];
+    const Dev &d = devs[blockIdx.y];
+    bus_body<FUSED>(d, zsel_arg, beta_arg, red);
 }
 
 // Partitioned mode, after the all-gather: install the received xbar halves of the ghost

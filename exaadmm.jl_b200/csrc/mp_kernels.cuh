@@ -34,8 +34,8 @@ constexpr int MP_FIN_BLOCK = 256;
 constexpr int MP_FIN_MAXB = 64;
 
 // ---------------------------------------------------------------------------
-// x-update of the generators of period t = blockIdx.y + 1 (mpacopf_admm_update_x_gpu.jl:9-31 ->
-// auglag_generator_kernel). Period 1 keeps the closed-form update inside k_xupdate.
+// x-update of the generators of period t = blockIdx.y (mpacopf_admm_update_x_gpu.jl:1-31): period 1
+// closed form, periods >= 2 auglag_generator_kernel.
 //   major_arg > 0: step-wise call; == 0: fused loop, read from the model-level control block.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(GBLOCK)
@@ -47,10 +47,14 @@ k_mp_gen(MpDev m, branch::PowTable T, long long major_arg, int zsel_arg, int max
         major = m.ctrl->inner + 1;
         zsel = m.ctrl->zsel;
     }
-    const int t = blockIdx.y + 1;
+    const int t = blockIdx.y;
     const int k = blockIdx.x * GBLOCK + threadIdx.x;
     if (k >= m.ngen) return;
     const Dev &d = m.devs[t];
+    if (t == 0) {                          // period 1: the plain closed-form update (mpacopf_admm_update_x_gpu.jl:8)
+        generator_update(d, d.zbuf[zsel], k);
+        return;
+    }
     const double *vprev = m.devs[t - 1].v;
     const size_t o = (size_t)t * m.ngen + k;
     const double2 v = *reinterpret_cast<const double2 *>(d.v + 2 * k);
@@ -77,6 +81,90 @@ k_mp_gen(MpDev m, branch::PowTable T, long long major_arg, int zsel_arg, int max
     m.r_s[o] = x[2];
     m.g_mu[o] = mu;
     m.g_xi[o] = xi;
+}
+
+// ---------------------------------------------------------------------------
+// Branch x-update of ALL periods in one persistent launch: the work queue runs over the T x nline
+// (period, branch) pairs, so the device sees T times the work of a single-period launch and ONE tail
+// (the serial chain of the slowest branch) instead of T. Same lane state machine as k_xupdate
+// (kernels.cuh); only the bookkeeping of which period a lane's branch belongs to is added.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(XBLOCK, EA_XMINB)
+k_xupdate_mp(MpDev m, int nline, branch::PowTable T, long long major_arg, int zsel_arg, int max_auglag, double mu_max,
+             double scale) {
+    extern __shared__ double tile[];                       // TILE_ROWS x XBLOCK
+    long long major = major_arg;
+    int zsel = zsel_arg;
+    if (major_arg == 0) {
+        if (m.ctrl->done) return;
+        major = m.ctrl->inner + 1;
+        zsel = m.ctrl->zsel;
+    }
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int total = m.T * nline;
+    double *col = tile + threadIdx.x;
+    const branch::Objective<branch::TileView<XBLOCK>> eval{ { col }, scale };
+    branch::Lane L;
+    L.phase = branch::NEED;
+    L.step_pending = false;
+    int G = -1;                                             // (period, branch) pair of this lane: G = t * nline + I
+    unsigned long long work[7] = { 0, 0, 0, 0, 0, 0, 0 };
+    int mx = 0;
+    Counters *counters = m.devs[0].counters;
+    const int count_work = m.devs[0].count_work;
+
+#pragma unroll 1
+    for (;;) {
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool need = (L.phase == branch::NEED);
+            const unsigned mk = __ballot_sync(full, need);
+            if (mk) {
+                int base = 0;
+                if (lane == __ffs(mk) - 1) base = atomicAdd(&m.ctrl->next_line, __popc(mk));
+                base = __shfl_sync(full, base, __ffs(mk) - 1);
+                if (need) {
+                    G = base + __popc(mk & ((1u << lane) - 1u));
+                    if (G < total) {
+                        const int t = G / nline;
+                        const Dev &d = m.devs[t];
+                        load_branch(d, d.zbuf[zsel], G - t * nline, major, col, L);
+                        branch::begin(L, T);
+                    } else L.phase = branch::DONE;
+                }
+            }
+            double xl[6], xu[6];
+            load_bounds(col, xl, xu);
+            if (branch::eval_pass(L, eval, pass, xl, xu, max_auglag, mu_max, T)) {
+                const int t = G / nline;
+                store_branch(m.devs[t], G - t * nline, L);
+                work[0] += 1; work[1] += L.it_al; work[2] += L.evals; work[3] += L.cg; work[4] += L.shifts;
+                work[5] += L.rejected; work[6] += L.hit_max;
+                mx = max(mx, L.evals);
+                L.phase = branch::NEED;
+            }
+        }
+        if (__all_sync(full, L.phase == branch::DONE || L.phase == branch::NEED)) {
+            if (__all_sync(full, L.phase == branch::DONE)) break;
+        }
+        double xl[6], xu[6];
+        load_bounds(col, xl, xu);
+        branch::compute(L, xl, xu);
+    }
+    if (count_work) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) work[k] += __shfl_down_sync(full, work[k], o);
+            mx = max(mx, __shfl_down_sync(full, mx, o));
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) if (work[k]) atomicAdd(&counters->v[k], work[k]);
+            atomicMax(&counters->v[7], (unsigned long long)mx);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -146,6 +234,7 @@ __global__ void __launch_bounds__(MP_FIN_BLOCK) k_mp_finish(MpDev m) {
         c->zsel = zsel ^ 1;
         const int done = (top[0] <= c->eps_pri || inner >= c->inner_limit) ? 1 : 0;
         c->done = done;
+        c->next_line = 0;
         for (int t = 0; t < m.T; ++t) {
             Ctrl *p = m.pctrl[t];
             p->inner = inner; p->zsel = zsel ^ 1; p->next_line = 0; p->done = done;

@@ -26,8 +26,8 @@ class Load:
 def get_load(prefix, load_scale: float = 1.0) -> Load:
     """``get_load(name)`` (opfdata.jl:121-130): reads ``<prefix>.Pd`` and ``<prefix>.Qd``
     (whitespace-delimited, one row per bus, one column per period)."""
-    pd = np.atleast_2d(np.loadtxt(str(prefix) + ".Pd"))
-    qd = np.atleast_2d(np.loadtxt(str(prefix) + ".Qd"))
+    pd = np.loadtxt(str(prefix) + ".Pd", ndmin=2)           # a single-period file is one column, not one row
+    qd = np.loadtxt(str(prefix) + ".Qd", ndmin=2)
     if pd.shape != qd.shape:
         raise ValueError("Pd and Qd profiles differ in shape")
     return Load(pd * load_scale, qd * load_scale)

@@ -163,7 +163,7 @@ def test_case9_three_periods_known_answer(tmp_path, case9_grid, mode):
 def test_warm_start_solve_matches_oracle(tmp_path, case9_grid):
     """solve_mpacopf's default warm start: every period solved alone first (keeps the line-limit multipliers),
     then init_solution! and the coupled solve (solve_mpacopf.jl:27-35)."""
-    scales = [1.0, 0.96, 1.04]
+    scales = [1.0, 0.975, 1.025]          # the 2 % ramp limit binds for two generators between periods 2 and 3
     prefix = write_profile(tmp_path, case9_grid, scales)
     env, mod = solve_mpacopf(ea.CASE9, prefix, use_gpu=True, verbose=0, end_period=3, outer_iterlim=25, outer_eps=2e-5)
     par = Parameters(); par.verbose = 0; par.outer_iterlim = 25; par.outer_eps = 2e-5
@@ -176,10 +176,12 @@ def test_warm_start_solve_matches_oracle(tmp_path, case9_grid):
     assert mod.info.status == "Solved" and oinfo.status == 2
     assert mod.info.objval == pytest.approx(oinfo.objval, rel=1e-8)
     _compare_state(mod, om, 1e-6, "final state")
-    # the ramp constraint is what couples the periods: it must hold and, with a 4 % load swing, bind somewhere
+    # the ramp constraint is what couples the periods: it holds to the ADMM tolerance and binds somewhere
     pg = np.array([m.solution.u_curr[0:2 * mod.ngen:2] for m in mod.models])
     ramp = 0.02 * np.asarray(case9_grid.pgmax)
-    assert np.all(np.abs(np.diff(pg, axis=0)) <= ramp + 1e-5)
+    step = np.abs(np.diff(pg, axis=0))
+    assert np.all(step <= ramp + 2e-4) and np.any(step >= 0.999 * ramp)
+    assert mod.info.user.err_ramp == pytest.approx(om.err_ramp, abs=1e-7)
     mod.close()
 
 
