@@ -209,36 +209,41 @@ __global__ void __launch_bounds__(MP_FIN_BLOCK) k_mp_finish(MpDev m) {
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // per-period norms, one thread per (period, norm): sqrt(||period vectors||^2 + ||ramp vectors||^2)
+    for (int i = threadIdx.x; i < 4 * m.T; i += MP_FIN_BLOCK) {
+        const int t = i >> 2, k = i & 3;
+        double n = sqrt(__ldcg(&m.sums[i]));
+        if (t > 0) {
+            double s = 0.0;
+            for (int b = 0; b < nbx; ++b) s += __ldcg(&m.partials[((size_t)(t - 1) * 4 + k) * nbx + b]);
+            const double rn = sqrt(s);
+            n = sqrt(n * n + rn * rn);
+        }
+        m.res_t[i] = n;
+    }
+    __syncthreads();
+    __shared__ int s_done;
+    __shared__ long long s_inner;
+    if (threadIdx.x < 4) {                                   // max over periods (mpacopf_admm_update_residual_gpu.jl:54-59)
+        double top = 0.0;
+        for (int t = 0; t < m.T; ++t) top = fmax(top, m.res_t[4 * t + threadIdx.x]);
+        c->res[threadIdx.x] = top;
+        if (threadIdx.x == 0) {
+            const long long inner = c->inner + 1;
+            s_inner = inner;
+            s_done = (top <= c->eps_pri || inner >= c->inner_limit) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < m.T; t += MP_FIN_BLOCK) {
+        Ctrl *p = m.pctrl[t];
+        p->inner = s_inner; p->zsel = zsel ^ 1; p->next_line = 0; p->done = s_done;
+    }
     if (threadIdx.x == 0) {
-        double top[4] = { 0.0, 0.0, 0.0, 0.0 };
-        for (int t = 0; t < m.T; ++t) {
-            double n[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) n[k] = sqrt(__ldcg(&m.sums[4 * t + k]));
-            if (t > 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    double s = 0.0;
-                    for (int b = 0; b < nbx; ++b) s += __ldcg(&m.partials[((size_t)(t - 1) * 4 + k) * nbx + b]);
-                    const double rn = sqrt(s);
-                    n[k] = sqrt(n[k] * n[k] + rn * rn);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { m.res_t[4 * t + k] = n[k]; top[k] = fmax(top[k], n[k]); }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) c->res[k] = top[k];
-        const long long inner = c->inner + 1;
-        c->inner = inner;
+        c->inner = s_inner;
         c->zsel = zsel ^ 1;
-        const int done = (top[0] <= c->eps_pri || inner >= c->inner_limit) ? 1 : 0;
-        c->done = done;
+        c->done = s_done;
         c->next_line = 0;
-        for (int t = 0; t < m.T; ++t) {
-            Ctrl *p = m.pctrl[t];
-            p->inner = inner; p->zsel = zsel ^ 1; p->next_line = 0; p->done = done;
-        }
         *m.ticket = 0u;
     }
 }

@@ -29,6 +29,7 @@ struct orc_mp {
     double **gen_membuf;                            /* T x (8 x ngen) */
     double (*res)[4];                               /* per-period residual norms (models[i].info) */
     double *norm_z_prev;                            /* per period */
+    int64_t gen_cnt[5];                             /* generator sub-problems: calls, AL iterations, f-evaluations, max AL its, max evals of one call */
 };
 
 static double mp_dmin(double a, double b) { return a < b ? a : b; }
@@ -87,6 +88,7 @@ double *orc_mp_ramp_vector(orc_mp_t *mp, int32_t t, int f) {
 }
 double *orc_mp_gen_membuf(orc_mp_t *mp, int32_t t) { return (t >= 0 && t < mp->T) ? mp->gen_membuf[t] : NULL; }
 int64_t orc_mp_nvar(const orc_mp_t *mp) { return mp->nvar; }
+void orc_mp_gen_counters(const orc_mp_t *mp, int64_t out[5]) { memcpy(out, mp->gen_cnt, sizeof(mp->gen_cnt)); }
 
 /* mpacopf_init_solution_cpu.jl:1-21 */
 void orc_mp_init_solution(orc_mp_t *mp, double rho_pq, double rho_va) {
@@ -221,7 +223,11 @@ static void gen_ramp_update(orc_mp_t *mp, int t, int64_t major_iter, int32_t max
         param[4] = v[pg] - z[pg];
         param[5] = r_v[pg] - r_z[I];
         if (major_iter <= 1) param[7] = 10.0;
-        orc_gen_ramp_solve(x, xl, xu, param, m->c2[I], m->c1[I], m->c0[I], m->baseMVA, scale, max_auglag, xi_max, NULL);
+        int32_t work[3];
+        orc_gen_ramp_solve(x, xl, xu, param, m->c2[I], m->c1[I], m->c0[I], m->baseMVA, scale, max_auglag, xi_max, work);
+        mp->gen_cnt[0]++; mp->gen_cnt[1] += work[0]; mp->gen_cnt[2] += work[1];
+        if (work[0] > mp->gen_cnt[3]) mp->gen_cnt[3] = work[0];
+        if (work[1] > mp->gen_cnt[4]) mp->gen_cnt[4] = work[1];
         u[pg] = x[0];
         r_u[I] = x[1];
         r_s[I] = x[2];

@@ -33,6 +33,9 @@ orc_model_t *orc_mp_period(orc_mp_t *mp, int32_t t);            /* 0-based perio
 double *orc_mp_ramp_vector(orc_mp_t *mp, int32_t t, int field); /* ngen doubles, borrowed    */
 double *orc_mp_gen_membuf(orc_mp_t *mp, int32_t t);             /* 8 x ngen column-major     */
 int64_t orc_mp_nvar(const orc_mp_t *mp);
+/* work of the generator sub-problems so far: calls, AL iterations, f-evaluations, largest AL count and largest
+ * f-evaluation count of one call */
+void   orc_mp_gen_counters(const orc_mp_t *mp, int64_t out[5]);
 
 void   orc_mp_init_solution(orc_mp_t *mp, double rho_pq, double rho_va);
 double orc_mp_outer_prestep(orc_mp_t *mp);
