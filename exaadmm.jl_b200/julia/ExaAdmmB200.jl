@@ -160,4 +160,46 @@ function admm_two_level(env::Env, mod::Mod, device=nothing)
     return
 end
 
+# ---- multi-period model: ModelMpacopf{Float64,TD,TI,TM} (src/models/mpacopf/) ---------------------
+# The model's constructor calls ea_mp_create (loads period-major) and wraps ea_mp_period(h, t) as the handles of
+# mod.models[t+1]; mod.solution[i].<field> are B200RampVector(handle, period, field) with copyto! ->
+# ea_mp_get_ramp_vector / ea_mp_set_ramp_vector. One method per generic function, as for the single-period model:
+const MpMod = ModelMpacopf{Float64,TD,TI,TM}
+mp_handle(mod::MpMod) = mod.models[1].gen_solution.handle      # the ea_mp_handle_t* is kept in the gen_solution slot
+mp_check(h, rc) = rc == 0 || error(unsafe_string(ccall((:ea_mp_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
+
+function admm_update_x(env::Env, mod::MpMod, device=nothing)
+    p = env.params
+    mp_check(mp_handle(mod), ccall((:ea_mp_update_x, LIB), Cint, (Ptr{Cvoid}, Int64, Int32, Cdouble, Cdouble),
+                                   mp_handle(mod), mod.info.inner, p.max_auglag, p.mu_max, p.scale)); return
+end
+admm_update_xbar(env::Env, mod::MpMod, device=nothing) =
+    (mp_check(mp_handle(mod), ccall((:ea_mp_update_xbar, LIB), Cint, (Ptr{Cvoid},), mp_handle(mod))); nothing)
+admm_update_z(env::Env, mod::MpMod, device=nothing) =
+    (mp_check(mp_handle(mod), ccall((:ea_mp_update_z, LIB), Cint, (Ptr{Cvoid}, Cdouble), mp_handle(mod), env.params.beta)); nothing)
+admm_update_l(env::Env, mod::MpMod, device=nothing) =
+    (mp_check(mp_handle(mod), ccall((:ea_mp_update_l, LIB), Cint, (Ptr{Cvoid}, Cdouble), mp_handle(mod), env.params.beta)); nothing)
+admm_update_lz(env::Env, mod::MpMod, device=nothing) =
+    (mp_check(mp_handle(mod), ccall((:ea_mp_update_lz, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble), mp_handle(mod),
+                                    env.params.beta, env.params.MAX_MULTIPLIER)); nothing)
+function admm_update_residual(env::Env, mod::MpMod, device=nothing)
+    out = zeros(4)
+    mp_check(mp_handle(mod), ccall((:ea_mp_update_residual, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), mp_handle(mod), out))
+    mod.info.primres, mod.info.dualres, mod.info.norm_z_curr, mod.info.mismatch = out; return
+end
+function admm_two_level(env::Env, mod::MpMod, device=nothing)       # the whole loop in one ccall
+    p = env.params
+    par = EaParams(p.mu_max, p.max_auglag, p.verbose, p.initial_beta, p.inc_c, p.theta, p.outer_eps,
+                   p.MAX_MULTIPLIER, p.scale, p.obj_scale, p.outer_iterlim, p.inner_iterlim)
+    info = EaInfo(); err = Ref{Cdouble}(0)
+    mp_check(mp_handle(mod), ccall((:ea_mp_admm_two_level, LIB), Cint, (Ptr{Cvoid}, Ref{EaParams}, Ref{EaInfo}, Ref{Cdouble}),
+                                   mp_handle(mod), par, info, err))
+    i = mod.info
+    i.status = (:NotSpecified, :IterationLimit, :Solved)[info.status + 1]
+    i.inner, i.outer, i.cumul, i.objval, i.mismatch = info.inner, info.outer, info.cumul, info.objval, info.mismatch
+    i.primres, i.dualres, i.norm_z_curr, i.norm_z_prev = info.primres, info.dualres, info.norm_z_curr, info.norm_z_prev
+    i.time_overall = info.time_overall; i.user.err_ramp = err[]; p.beta = info.beta
+    return
+end
+
 end # module
