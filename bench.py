@@ -64,6 +64,14 @@ def make_grid(workload):
     return ea.GridData.from_opfdata(data, tight_factor=0.99), data
 
 
+def base_config(workload, grid, par, rho_pq, rho_va):
+    """The part of `config` both arms share (same workload, same algorithm parameters)."""
+    return {"workload": f"{workload}-like synthetic grid (seed=nbus; real MATPOWER file unavailable offline)",
+            "nbus": grid.nbus, "ngen": grid.ngen, "nline": grid.nline, "nvar": 2 * grid.ngen + 8 * grid.nline,
+            "rho_pq": rho_pq, "rho_va": rho_va, "scale": par.scale, "obj_scale": par.obj_scale, "tight_factor": 0.99,
+            "outer_iterlim": 20, "inner_iterlim": 1000}
+
+
 def default_params(workload):
     from exaadmm_b200.environment import Parameters
     _, rho_pq, rho_va, scale = WORKLOADS[workload]
@@ -146,8 +154,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "admm_inner_iterations_per_sec", "value": val, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}-like synthetic (seed=nbus)", "rho_pq": rho_pq, "rho_va": rho_va,
-                   "scale": par.scale, "nbus": grid.nbus, "ngen": grid.ngen, "nline": grid.nline},
+        "config": dict(base_config(args.workload, grid, par, rho_pq, rho_va),
+                       parallelism=f"{threads} host threads (OpenMP over branches and buses), rank 0 only"),
         "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": threads, "kind": "port",
                          "sample": f"first {args.warmup}+{args.steps} inner iterations of the solve, full grid, "
                                    f"OpenMP over branches and buses (oracle restatement, not Julia)"},
@@ -372,10 +380,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": "admm_inner_iterations_per_sec", "value": value, "unit": "iterations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / ran,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}-like synthetic grid (seed=nbus; real MATPOWER file unavailable offline)",
-                   "nbus": grid.nbus, "ngen": grid.ngen, "nline": grid.nline, "nvar": nvar, "rho_pq": rho_pq,
-                   "rho_va": rho_va, "scale": par.scale, "obj_scale": par.obj_scale, "tight_factor": 0.99,
-                   "outer_iterlim": 20, "inner_iterlim": 1000,
+        "config": {**base_config(args.workload, grid, par, rho_pq, rho_va),
                    "parallelism": "1 GPU" if world == 1 else f"{world} independent load scenarios (loads x U[0.99,1.01]), one per GPU, no collective",
                    "l2_policy": "working set (15 vectors x 5.8 MB + grid) is below the 126 MB L2; iterations are "
                                 "data-dependent (each reads what the previous wrote), no artificial flush",
