@@ -76,6 +76,39 @@ class EaCounters(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+_QP_FIELDS = ("Hs", "LH_1h", "RH_1h", "LH_1i", "RH_1i", "LH_1j", "RH_1j", "LH_1k", "RH_1k", "ls", "us", "line_res",
+              "pgmax", "pgmin", "qgmax", "qgmin", "c1", "c2", "Pd", "Qd")
+QP_ARRAYS = {"sqp_line": (0, 6), "qpsub_membuf": (1, 5), "lambda": (2, 4)}      # enum ea_qp_array: (id, rows)
+
+
+class EaQpsubData(C.Structure):
+    """``ea_qpsub_data_t``: the fields the SQP driver fills in on ``ModelQpsub`` (qpsub_model.jl:63-92)."""
+    _fields_ = [(n, _pd) for n in _QP_FIELDS]
+
+
+def make_qpsub_struct(d, nline: int, ngen: int, nbus: int):
+    """``d``: any object with the ``_QP_FIELDS`` attributes in the reference's shapes (Hs (6 nline, 6), LH_1h (nline, 4),
+    ls (nline, 6), line_res (4, nline) or None, ...). Returns (struct, keepalive)."""
+    shapes = {"Hs": (6 * nline, 6), "LH_1h": (nline, 4), "LH_1i": (nline, 4), "LH_1j": (nline, 2), "LH_1k": (nline, 2),
+              "RH_1h": (nline,), "RH_1i": (nline,), "RH_1j": (nline,), "RH_1k": (nline,), "ls": (nline, 6),
+              "us": (nline, 6), "pgmax": (ngen,), "pgmin": (ngen,), "qgmax": (ngen,), "qgmin": (ngen,), "c1": (ngen,),
+              "c2": (ngen,), "Pd": (nbus,), "Qd": (nbus,)}
+    s, keep = EaQpsubData(), []
+    for n in _QP_FIELDS:
+        a = getattr(d, n, None)
+        if n == "line_res":
+            if a is None:
+                continue                                   # NULL = zeros
+            a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(4, nline).T)   # -> nline x 4
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != shapes[n]:
+                raise ValueError(f"qpsub field {n}: shape {a.shape}, expected {shapes[n]}")
+        keep.append(a)
+        setattr(s, n, a.ctypes.data_as(_pd))
+    return s, keep
+
+
 def make_grid_struct(g: GridData):
     """Build an ``ea_grid_t`` whose pointers borrow the numpy arrays of ``g``.
     Returns (struct, keepalive)."""
@@ -181,6 +214,25 @@ SIGNATURES = {
                                   C.POINTER(C.c_int64), _pd]),
     "ea_mp_admm_two_level": (C.c_int, [_H, C.POINTER(EaParams), C.POINTER(EaInfo), _pd]),
     "ea_mp_get_kernel_times": (C.c_int, [_H, _pd]),
+    # one-level ADMM on the SQP sub-problem (ModelQpsub)
+    "ea_qp_last_error": (C.c_char_p, [_H]),
+    "ea_qp_create": (C.c_int, [C.POINTER(EaGrid), C.POINTER(EaQpsubData), C.c_int, C.POINTER(_H)]),
+    "ea_qp_destroy": (None, [_H]),
+    "ea_qp_nvar": (C.c_int64, [_H]),
+    "ea_qp_init_solution": (C.c_int, [_H, C.c_double, C.c_double]),
+    "ea_qp_get_vector": (C.c_int, [_H, C.c_int, _pd, C.c_int64]),
+    "ea_qp_set_vector": (C.c_int, [_H, C.c_int, _pd, C.c_int64]),
+    "ea_qp_get_line_array": (C.c_int, [_H, C.c_int, _pd, C.c_int64]),
+    "ea_qp_set_line_array": (C.c_int, [_H, C.c_int, _pd, C.c_int64]),
+    "ea_qp_update_x": (C.c_int, [_H, C.c_int64, C.c_int32, C.c_double, C.c_double]),
+    "ea_qp_update_xbar": (C.c_int, [_H]),
+    "ea_qp_update_l_single": (C.c_int, [_H]),
+    "ea_qp_update_residual": (C.c_int, [_H, _pd]),
+    "ea_qp_poststep": (C.c_int, [_H, _pd, _pd, _pd, _pd, _pd]),
+    "ea_qp_admm_one_level": (C.c_int, [_H, C.POINTER(EaParams), C.POINTER(EaInfo)]),
+    "ea_qp_set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
+    "ea_qp_get_counters": (C.c_int, [_H, C.POINTER(C.c_int64)]),
+    "ea_qp_get_kernel_times": (C.c_int, [_H, _pd]),
     "ea_diag_fp64_peak": (C.c_int, [C.c_int, _pd]),
     "ea_diag_branch_eval": (C.c_int, [C.c_int, C.c_int64, _pd, _pd, _pd, C.c_double, _pd, _pd, _pd]),
 }

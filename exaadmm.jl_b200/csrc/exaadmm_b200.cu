@@ -4,6 +4,7 @@
 #include "../../include/exaadmm_b200.h"
 #include "kernels.cuh"
 #include "mp_kernels.cuh"
+#include "qp_kernels.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -1102,3 +1103,4 @@ int ea_diag_fp64_peak(int device, double *tflops) {
 }  // extern "C"
 
 #include "mp_host.inc"
+#include "qp_host.inc"

@@ -21,6 +21,9 @@ def _mp(mod):
     if getattr(mod, "is_multiperiod", False):
         from . import mpacopf
         return mpacopf
+    if getattr(mod, "is_qpsub", False):         # ModelQpsub methods (src/models/qpsub/), implemented in qpsub.py
+        from . import qpsub
+        return qpsub
     return None
 
 
@@ -92,6 +95,13 @@ def admm_update_xbar(env, mod, device=None):
     if _mp(mod):
         return _mp(mod).admm_update_xbar(env, mod)
     mod._check(mod.lib.ea_update_xbar(mod.h))
+
+
+def admm_update_l_single(env, mod, device=None):
+    """One-level ADMM only (qpsub_admm_update_l_single_gpu.jl); defined for ``ModelQpsub``."""
+    if not getattr(mod, "is_qpsub", False):
+        raise TypeError("admm_update_l_single has a method for ModelQpsub only (as in the reference)")
+    return _mp(mod).admm_update_l_single(env, mod)
 
 
 def admm_update_z(env, mod, device=None):

@@ -314,6 +314,75 @@ int  ea_mp_admm_two_level(ea_mp_handle_t *h, const ea_params_t *par, ea_info_t *
  * inner iterations executed, 0 }. */
 int  ea_mp_get_kernel_times(ea_mp_handle_t *h, double out[4]);
 
+/* ---- one-level ADMM on the SQP sub-problem: `ModelQpsub` (src/models/qpsub/, src/algorithms/admm_one_level.jl;
+ * SURVEY.md section 8f row 4) -----------------------------------------------------------------------------------
+ * The QP of one SQP iteration of ACOPF, decomposed like the ACOPF itself: generators (closed form with shifted
+ * bounds / costs), buses (the same consensus update with shifted loads) and branches - per branch a box-constrained
+ * QP in (t_ij, t_ji, w_i, w_j, theta_i, theta_j) built from the SQP Hessian block and the linearised constraints
+ * 1h / 1i (eliminated) and 1j / 1k (line limits, augmented Lagrangian), solved by TRON.
+ * ea_qpsub_data_t carries the fields the SQP driver fills in on `ModelQpsub` (qpsub_model.jl:63-92), row-major:
+ * Hs nline x 6 x 6 (variables w_ijR, w_ijI, w_i, w_j, theta_i, theta_j), LH_1h / LH_1i nline x 4, LH_1j / LH_1k
+ * nline x 2, RH_* nline, ls / us nline x 6, line_res nline x 4 (NULL = zeros), generator arrays ngen, Pd / Qd nbus. */
+typedef struct ea_qpsub_data {
+    const double *Hs;
+    const double *LH_1h, *RH_1h, *LH_1i, *RH_1i, *LH_1j, *RH_1j, *LH_1k, *RH_1k;
+    const double *ls, *us;
+    const double *line_res;
+    const double *pgmax, *pgmin, *qgmax, *qgmin, *c1, *c2;
+    const double *Pd, *Qd;
+} ea_qpsub_data_t;
+
+/* per-line arrays of ModelQpsub readable with ea_qp_get_line_array */
+enum ea_qp_array {
+    EA_QP_SQP_LINE = 0,   /* 6 x nline: w_ijR, w_ijI, w_i, w_j, theta_i, theta_j of the last branch solve (mod.sqp_line) */
+    EA_QP_MEMBUF = 1,     /* 5 x nline: lambda_1h, lambda_1i, lambda_1j, lambda_1k, penalty (mod.qpsub_membuf)          */
+    EA_QP_LAMBDA = 2      /* 4 x nline: multipliers of 14h, 14i, 14j, 14k handed back to the SQP (mod.lambda)            */
+};
+
+typedef struct ea_qp_handle ea_qp_handle_t;
+const char *ea_qp_last_error(const ea_qp_handle_t *h);
+/* ModelQpsub{T,TD,TI,TM}(env) (qpsub_model.jl:133-310) + the field copies of solve_qpsub (solve_qpsub.jl:83-104).
+ * Hs must be symmetric (the SQP driver builds it so; the device code reads the lower triangle). obj_scale is inert
+ * on this path, as in the reference (solve_qpsub stores it after the constructor's scaling step has run). */
+int  ea_qp_create(const ea_grid_t *grid, const ea_qpsub_data_t *data, int device, ea_qp_handle_t **out);
+void ea_qp_destroy(ea_qp_handle_t *h);
+int64_t ea_qp_nvar(const ea_qp_handle_t *h);
+/* init_solution! (qpsub_init_solution_gpu.jl:1-98) */
+int  ea_qp_init_solution(ea_qp_handle_t *h, double rho_pq, double rho_va);
+/* Solution fields (enum ea_field; EA_V_PREV is mod.v_prev), reference layout, n = nvar. */
+int  ea_qp_get_vector(ea_qp_handle_t *h, int field, double *host, int64_t n);
+int  ea_qp_set_vector(ea_qp_handle_t *h, int field, const double *host, int64_t n);
+/* which = enum ea_qp_array; rows x nline, column-major like the reference's matrices (n = rows * nline). */
+int  ea_qp_get_line_array(ea_qp_handle_t *h, int which, double *host, int64_t n);
+int  ea_qp_set_line_array(ea_qp_handle_t *h, int which, const double *host, int64_t n);
+/* admm_update_x: generator_kernel_two_level on the qpsub bounds / costs (qpsub_generator_kernel_gpu.jl), then
+ * auglag_linelimit_qpsub (qpsub_auglag_Ab_linelimit_kernel_red_gpu.jl + qpsub_tron_linelimit_kernel.jl).
+ * inner = info.inner (the penalty restarts at 10 when it is 1). */
+int  ea_qp_update_x(ea_qp_handle_t *h, int64_t inner, int32_t max_auglag, double mu_max, double scale);
+/* admm_update_xbar: v_prev <- v_curr, then the bus kernel with qpsub_Pd / qpsub_Qd (qpsub_admm_update_xbar_gpu.jl). */
+int  ea_qp_update_xbar(ea_qp_handle_t *h);
+/* admm_update_l_single: l += rho (u - v) (qpsub_admm_update_l_single_gpu.jl). */
+int  ea_qp_update_l_single(ea_qp_handle_t *h);
+/* admm_update_residual (qpsub_admm_update_residual_gpu.jl): out = { primres, dualres, mismatch, objval, auglag }. */
+int  ea_qp_update_residual(ea_qp_handle_t *h, double out[5]);
+/* admm_poststep (qpsub_admm_prepoststep_gpu.jl): objval / auglag and what is handed back to the SQP driver:
+ * dw_sol, dtheta_sol (nbus each: averages over the incident branch ends) and dual_infeas (ngen + 6 nline). Any
+ * pointer may be NULL. The other outputs of the reference are views of the state: dpg_sol / dqg_sol / dline_fl are
+ * entries of u_curr, dline_var is sqp_line, lambda is EA_QP_LAMBDA. */
+int  ea_qp_poststep(ea_qp_handle_t *h, double *objval, double *auglag, double *dw_sol, double *dtheta_sol,
+                    double *dual_infeas);
+/* admm_one_level end to end (admm_one_level.jl:1-81): every iteration and the termination test run on the device
+ * (3 launches per iteration, replayed from a CUDA graph of `chunk` iterations; the host polls once per chunk).
+ * par->outer_iterlim, outer_eps, max_auglag, mu_max, scale are read; inner_iterlim is 1 and beta 0 by definition. */
+int  ea_qp_admm_one_level(ea_qp_handle_t *h, const ea_params_t *par, ea_info_t *info);
+/* "chunk" (iterations per graph replay, default 32), "use_graph" (0/1, default 1), "count_work" (0/1, default 1) */
+int  ea_qp_set_option(ea_qp_handle_t *h, const char *name, double value);
+/* out = { branch sub-problems solved, AL iterations (TRON solves), objective evaluations, largest AL count of one
+ * call } since creation */
+int  ea_qp_get_counters(ea_qp_handle_t *h, int64_t out[4]);
+/* out = { device seconds inside ea_qp_admm_one_level, iterations executed there, kernels launched, graph replays } */
+int  ea_qp_get_kernel_times(ea_qp_handle_t *h, double out[4]);
+
 int  ea_get_counters(ea_handle_t *h, ea_counters_t *out);
 int  ea_reset_counters(ea_handle_t *h);
 /* Options: "count_work" (0/1, atomics for ea_counters_t in the branch kernel, default 1),

@@ -446,8 +446,9 @@ static void dspcg(int n, double *x, const double *xl, const double *xu, const do
 
 /* B.0 driver: acopf_tron_linelimit_kernel.jl:44-148 around ExaTron.dtron,
  * == ExaTron.solveProblem on the CPU path (acopf_auglag_linelimit_kernel_cpu.jl:104-117). */
-int orc__tron_cb(int n, double *x, const double *xl, const double *xu, orc__f_fn evalf, orc__gh_fn evalgh,
-                 const void *ctx, int max_feval, int max_minor, double gtol, int *minor_out, tron_stats_t *st) {
+int orc__tron_cb_g(int n, double *x, const double *xl, const double *xu, orc__f_fn evalf, orc__gh_fn evalgh,
+                   const void *ctx, int max_feval, int max_minor, double gtol, int *minor_out, tron_stats_t *st,
+                   double *g_out) {
     const double eta0 = 1e-4, eta1 = 0.25, eta2 = 0.75, sigma1 = 0.25, sigma2 = 0.5, sigma3 = 4.0;
     const double frtol = 1e-12, fatol = 0.0, fmin = -1e32, cgtol = 0.1;
     const int cg_itermax = n;
@@ -468,7 +469,7 @@ int orc__tron_cb(int n, double *x, const double *xl, const double *xu, orc__f_fn
             const double prered = -(dot(n, s, g) + 0.5 * dot(n, s, wa));
             f = evalf(x, ctx);
             nfev++; st->nfev++;
-            if (nfev >= max_feval) { *minor_out = minor; return status; }
+            if (nfev >= max_feval) { *minor_out = minor; if (g_out) memcpy(g_out, g, sizeof(double) * (size_t)n); return status; }
             const double actred = fc - f;
             const double snorm = nrm2(n, s);
             if (iter == 1) delta = dmin(delta, snorm);
@@ -493,7 +494,12 @@ int orc__tron_cb(int n, double *x, const double *xl, const double *xu, orc__f_fn
         if (minor >= max_minor) { status = 1; break; }
     }
     *minor_out = minor;
+    if (g_out) memcpy(g_out, g, sizeof(double) * (size_t)n);   /* `tron.g`: the last gradient evaluated */
     return status;
+}
+int orc__tron_cb(int n, double *x, const double *xl, const double *xu, orc__f_fn evalf, orc__gh_fn evalgh,
+                 const void *ctx, int max_feval, int max_minor, double gtol, int *minor_out, tron_stats_t *st) {
+    return orc__tron_cb_g(n, x, xl, xu, evalf, evalgh, ctx, max_feval, max_minor, gtol, minor_out, st, NULL);
 }
 
 /* the branch instance of the driver: objective of acopf_eval_linelimit_kernel_cpu.jl */

@@ -18,8 +18,8 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(_HERE.parent))
-from exaadmm_b200.capi import (EaGrid, EaParams, EaInfo, EaCounters, FIELDS,  # noqa: E402
-                               make_grid_struct, params_struct)
+from exaadmm_b200.capi import (EaGrid, EaParams, EaInfo, EaCounters, EaQpsubData, FIELDS, QP_ARRAYS,  # noqa: E402
+                               make_grid_struct, make_qpsub_struct, params_struct)
 
 LIB_PATH = _HERE / "_build" / "libacopf_oracle.so"
 _pd = C.POINTER(C.c_double)
@@ -110,6 +110,28 @@ def lib():
         L.orc_mp_admm_two_level.restype = C.c_int
         L.orc_gen_ramp_solve.argtypes = [_pd, _pd, _pd, _pd, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.c_int32, C.c_double, C.POINTER(C.c_int32)]
+        # one-level ADMM on the SQP sub-problem (qpsub_oracle.h)
+        L.orc_qp_create.argtypes = [C.POINTER(EaGrid), C.POINTER(EaQpsubData), C.POINTER(H)]
+        L.orc_qp_create.restype = C.c_int
+        L.orc_qp_destroy.argtypes = [H]
+        L.orc_qp_set_threads.argtypes = [H, C.c_int]
+        L.orc_qp_nvar.argtypes = [H]
+        L.orc_qp_nvar.restype = C.c_int64
+        L.orc_qp_vector.argtypes = [H, C.c_int]
+        L.orc_qp_vector.restype = _pd
+        L.orc_qp_line_array.argtypes = [H, C.c_int]
+        L.orc_qp_line_array.restype = _pd
+        L.orc_qp_init_solution.argtypes = [H, C.c_double, C.c_double]
+        L.orc_qp_update_x.argtypes = [H, C.c_int64, C.c_int32, C.c_double, C.c_double]
+        L.orc_qp_update_xbar.argtypes = [H]
+        L.orc_qp_update_l_single.argtypes = [H]
+        L.orc_qp_update_residual.argtypes = [H, _pd]
+        L.orc_qp_poststep.argtypes = [H, _pd, _pd, _pd, _pd, _pd]
+        L.orc_qp_admm_one_level.argtypes = [H, C.POINTER(EaParams), C.POINTER(EaInfo)]
+        L.orc_qp_admm_one_level.restype = C.c_int
+        L.orc_qp_counters.argtypes = [H, C.POINTER(C.c_int64)]
+        L.orc_qp_branch_qp.argtypes = [_pd] * 8 + [C.c_double, _pd, C.c_double, _pd, C.c_double, _pd, C.c_double, _pd,
+                                                   C.c_double, _pd, _pd, _pd, _pd]
         _lib = L
     return _lib
 
@@ -335,3 +357,79 @@ class OracleMpModel:
         self.err_ramp = float(e[0])
         self.par.beta = info.beta
         return info
+
+
+class OracleQpModel:
+    """CPU-oracle twin of ``ModelQpsub`` (src/models/qpsub/) + its operator functions and ``admm_one_level``.
+
+    ``data``: object with the fields of ``exaadmm_b200.qpsub.QpsubData`` (reference shapes)."""
+
+    def __init__(self, grid, params, data, rho_pq: float, rho_va: float):
+        self.L = lib()
+        self.grid, self.par, self.data = grid, params, data
+        gs, self._keep = make_grid_struct(grid)
+        ds, self._keep2 = make_qpsub_struct(data, grid.nline, grid.ngen, grid.nbus)
+        h = C.c_void_p()
+        rc = self.L.orc_qp_create(C.byref(gs), C.byref(ds), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"orc_qp_create failed: {rc}")
+        self.h = h
+        self.nvar = int(self.L.orc_qp_nvar(h))
+        self.nline, self.ngen, self.nbus = grid.nline, grid.ngen, grid.nbus
+        self.L.orc_qp_init_solution(h, rho_pq, rho_va)
+        self.inner = self.outer = self.cumul = 0
+        self.res = np.zeros(5)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_qp_destroy(self.h)
+            self.h = None
+
+    def set_threads(self, n): self.L.orc_qp_set_threads(self.h, int(n))
+
+    def vec(self, name: str) -> np.ndarray:
+        return np.ctypeslib.as_array(self.L.orc_qp_vector(self.h, FIELDS[name]), shape=(self.nvar,))
+
+    def line_array(self, name: str) -> np.ndarray:
+        """``sqp_line`` (6 x nline), ``qpsub_membuf`` (5 x nline) or ``lambda`` (4 x nline), as in the reference."""
+        which, rows = QP_ARRAYS[name]
+        return np.ctypeslib.as_array(self.L.orc_qp_line_array(self.h, which), shape=(self.nline, rows)).T
+
+    def init_solution(self, rho_pq, rho_va): self.L.orc_qp_init_solution(self.h, rho_pq, rho_va)
+    def admm_increment_outer(self): self.outer += 1
+    def admm_increment_reset_inner(self): self.inner = 0
+    def admm_increment_inner(self): self.inner += 1; self.cumul += 1
+
+    def admm_update_x(self):
+        self.L.orc_qp_update_x(self.h, self.inner, self.par.max_auglag, self.par.mu_max, self.par.scale)
+
+    def admm_update_xbar(self): self.L.orc_qp_update_xbar(self.h)
+    def admm_update_l_single(self): self.L.orc_qp_update_l_single(self.h)
+
+    def admm_update_residual(self):
+        self.L.orc_qp_update_residual(self.h, _p(self.res))
+        return self.res.copy()
+
+    def admm_poststep(self) -> dict:
+        o, a = np.zeros(1), np.zeros(1)
+        dw, dt, di = np.zeros(self.nbus), np.zeros(self.nbus), np.zeros(self.ngen + 6 * self.nline)
+        self.L.orc_qp_poststep(self.h, _p(o), _p(a), _p(dw), _p(dt), _p(di))
+        u = self.vec("u_curr")
+        ls = 2 * self.ngen
+        return {"objval": float(o[0]), "auglag": float(a[0]), "dw_sol": dw, "dtheta_sol": dt, "dual_infeas": di,
+                "dpg_sol": u[0:ls:2].copy(), "dqg_sol": u[1:ls:2].copy(),
+                "dline_var": self.line_array("sqp_line").copy(),
+                "dline_fl": u[ls:].reshape(self.nline, 8)[:, :4].T.copy(), "lambda": self.line_array("lambda").copy()}
+
+    def admm_one_level(self) -> EaInfo:
+        info = EaInfo()
+        ps = params_struct(self.par)
+        rc = self.L.orc_qp_admm_one_level(self.h, C.byref(ps), C.byref(info))
+        if rc != 0:
+            raise RuntimeError(f"orc_qp_admm_one_level failed: {rc}")
+        return info
+
+    def counters(self) -> dict:
+        c = (C.c_int64 * 4)()
+        self.L.orc_qp_counters(self.h, c)
+        return dict(zip(("line_calls", "auglag_iters", "tron_evals", "max_auglag_one_call"), map(int, c)))

@@ -32,5 +32,9 @@ typedef double (*orc__f_fn)(const double *x, const void *ctx);
 typedef void (*orc__gh_fn)(const double *x, const void *ctx, double *g, double *A);
 int orc__tron_cb(int n, double *x, const double *xl, const double *xu, orc__f_fn evalf, orc__gh_fn evalgh,
                  const void *ctx, int max_feval, int max_minor, double gtol, int *minor_out, tron_stats_t *st);
+/* same; g_out (may be NULL) receives the last gradient the driver evaluated (`tron.g` after solveProblem) */
+int orc__tron_cb_g(int n, double *x, const double *xl, const double *xu, orc__f_fn evalf, orc__gh_fn evalgh,
+                   const void *ctx, int max_feval, int max_minor, double gtol, int *minor_out, tron_stats_t *st,
+                   double *g_out);
 
 #endif

@@ -4,6 +4,7 @@
 // free-set) against the oracle without a GPU. Not part of the product library.
 #include "../../exaadmm.jl_b200/csrc/branch.cuh"
 #include "../../exaadmm.jl_b200/csrc/genramp.cuh"
+#include "../../exaadmm.jl_b200/csrc/qpsub.cuh"
 #include <cmath>
 #include <cstring>
 
@@ -100,6 +101,35 @@ void hh_solve_gen(double *x, const double *xl, const double *xu, double *param, 
     for (int k = 0; k < 3; ++k) x[k] = xx[k];
     param[6] = mu; param[7] = xi;
     work[0] = it; work[1] = evals; work[2] = cg;
+}
+
+
+// One branch of the QP sub-problem model (qpsub.cuh). H: 6 x 6 row-major; l, rho, v, z: 8; Y: 8; res: 4;
+// lin = LH_1h[4], RH_1h, LH_1i[4], RH_1i, LH_1j[2], RH_1j, LH_1k[2], RH_1k; ls / us: 6; sq: sqp_line column (in / out);
+// mb: qpsub_membuf column (in / out); u: 8 out; lam: 4 out; work[3]: AL iterations, evaluations, cg iterations.
+void hh_solve_qp_branch(const double *H, const double *l, const double *rho, const double *v, const double *z,
+                        const double *Y, const double *res, const double *lin, const double *ls, const double *us,
+                        double *sq, double *mb, long long major_iter, int max_auglag, double mu_max, double scale,
+                        double *u, double *lam, int *work) {
+    branch::PowTable T;
+    make_pow_table(T, mu_max);
+    qpsub::Inputs in;
+    for (int i = 0; i < 6; ++i) for (int j = 0; j <= i; ++j) in.H[tron::tri(i, j)] = H[6 * i + j];
+    for (int k = 0; k < 8; ++k) { in.lam[k] = l[k]; in.rho[k] = rho[k]; in.xt[k] = v[k] - z[k]; in.Y[k] = Y[k]; }
+    for (int k = 0; k < 4; ++k) { in.res[k] = res[k]; in.LH_1h[k] = lin[k]; in.LH_1i[k] = lin[5 + k]; }
+    in.RH_1h = lin[4]; in.RH_1i = lin[9];
+    in.LH_1j[0] = lin[10]; in.LH_1j[1] = lin[11]; in.RH_1j = lin[12];
+    in.LH_1k[0] = lin[13]; in.LH_1k[1] = lin[14]; in.RH_1k = lin[15];
+    const double x0[4] = { sq[2], sq[3], sq[4], sq[5] }, xl[4] = { ls[2], ls[3], ls[4], ls[5] }, xu[4] = { us[2], us[3], us[4], us[5] };
+    double lam_j = mb[2], lam_k = mb[3], mu = (major_iter == 1) ? 10.0 : mb[4];
+    qpsub::ArrStore st;
+    qpsub::Result R;
+    qpsub::solve(in, st, x0, xl, xu, lam_j, lam_k, mu, max_auglag, mu_max, scale, T, R);
+    for (int k = 0; k < 8; ++k) u[k] = R.u[k];
+    for (int k = 0; k < 6; ++k) sq[k] = R.sqp[k];
+    for (int k = 0; k < 4; ++k) lam[k] = R.lambda[k];
+    mb[2] = lam_j; mb[3] = lam_k; mb[4] = mu;
+    work[0] = R.it; work[1] = R.evals; work[2] = R.cg;
 }
 
 }
