@@ -202,4 +202,78 @@ function admm_two_level(env::Env, mod::MpMod, device=nothing)       # the whole 
     return
 end
 
+# ---- one-level ADMM on the SQP sub-problem: ModelQpsub{Float64,TD,TI,TM} (src/models/qpsub/) --------------------
+# The SQP driver fills in the host fields of the model (mod.Hs ... mod.qpsub_Qd, plain Arrays for this tag) and calls
+# init_solution!, which is where they go to HBM: ea_qp_create (row-major copies: permutedims of the Julia matrices)
+# + ea_qp_init_solution. The ea_qp_handle_t* is kept in the gen_solution slot.
+const QpMod = ModelQpsub{Float64,TD,TI,TM}
+qp_handle(mod::QpMod) = mod.gen_solution.handle
+qp_check(h, rc) = rc == 0 || error(unsafe_string(ccall((:ea_qp_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
+struct EaQpsubData
+    Hs::Ptr{Cdouble}
+    LH_1h::Ptr{Cdouble}; RH_1h::Ptr{Cdouble}; LH_1i::Ptr{Cdouble}; RH_1i::Ptr{Cdouble}
+    LH_1j::Ptr{Cdouble}; RH_1j::Ptr{Cdouble}; LH_1k::Ptr{Cdouble}; RH_1k::Ptr{Cdouble}
+    ls::Ptr{Cdouble}; us::Ptr{Cdouble}; line_res::Ptr{Cdouble}
+    pgmax::Ptr{Cdouble}; pgmin::Ptr{Cdouble}; qgmax::Ptr{Cdouble}; qgmin::Ptr{Cdouble}; c1::Ptr{Cdouble}; c2::Ptr{Cdouble}
+    Pd::Ptr{Cdouble}; Qd::Ptr{Cdouble}
+end
+function init_solution!(mod::QpMod, sol, rho_pq::Float64, rho_va::Float64, device=nothing)
+    rm(a) = Array(permutedims(a))                       # (nline, k) column-major -> nline x k row-major
+    nl = mod.grid_data.nline
+    Hs = Array(permutedims(reshape(permutedims(mod.Hs), 6, 6, nl), (2, 1, 3)))    # nline blocks, each 6 x 6 row-major
+    keep = (Hs, rm(mod.LH_1h), mod.RH_1h, rm(mod.LH_1i), mod.RH_1i, rm(mod.LH_1j), mod.RH_1j, rm(mod.LH_1k), mod.RH_1k,
+            rm(mod.ls), rm(mod.us), Array(mod.line_res), mod.qpsub_pgmax, mod.qpsub_pgmin, mod.qpsub_qgmax,
+            mod.qpsub_qgmin, mod.qpsub_c1, mod.qpsub_c2, mod.qpsub_Pd, mod.qpsub_Qd)
+    GC.@preserve keep begin
+        data = EaQpsubData(map(pointer, keep)...)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        qp_check(C_NULL, ccall((:ea_qp_create, LIB), Cint, (Ref{EaGrid}, Ref{EaQpsubData}, Cint, Ref{Ptr{Cvoid}}),
+                               grid_struct(mod.grid_data), data, 0, h))
+    end
+    mod.gen_solution = B200Handle(h[], :ea_qp_destroy)   # finalizer -> ea_qp_destroy
+    qp_check(h[], ccall((:ea_qp_init_solution, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble), h[], rho_pq, rho_va)); return
+end
+function admm_update_x(env::Env, mod::QpMod, device=nothing)
+    p = env.params
+    qp_check(qp_handle(mod), ccall((:ea_qp_update_x, LIB), Cint, (Ptr{Cvoid}, Int64, Int32, Cdouble, Cdouble),
+                                   qp_handle(mod), mod.info.inner, p.max_auglag, p.mu_max, p.scale)); return
+end
+admm_update_xbar(env::Env, mod::QpMod, device=nothing) =
+    (qp_check(qp_handle(mod), ccall((:ea_qp_update_xbar, LIB), Cint, (Ptr{Cvoid},), qp_handle(mod))); nothing)
+admm_update_l_single(env::Env, mod::QpMod, device=nothing) =
+    (qp_check(qp_handle(mod), ccall((:ea_qp_update_l_single, LIB), Cint, (Ptr{Cvoid},), qp_handle(mod))); nothing)
+function admm_update_residual(env::Env, mod::QpMod, device=nothing)
+    out = zeros(5)
+    qp_check(qp_handle(mod), ccall((:ea_qp_update_residual, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), qp_handle(mod), out))
+    mod.info.primres, mod.info.dualres, mod.info.mismatch, mod.info.objval, mod.info.auglag = out; return
+end
+function admm_poststep(env::Env, mod::QpMod, device=nothing)
+    obj = Ref{Cdouble}(0); al = Ref{Cdouble}(0)
+    qp_check(qp_handle(mod), ccall((:ea_qp_poststep, LIB), Cint,
+                                   (Ptr{Cvoid}, Ref{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                                   qp_handle(mod), obj, al, mod.dw_sol, mod.dtheta_sol, mod.dual_infeas))
+    mod.info.objval, mod.info.auglag = obj[], al[]
+    u = zeros(mod.nvar); copyto!(u, mod.solution.u_curr)
+    ng, nl = mod.grid_data.ngen, mod.grid_data.nline
+    mod.dpg_sol .= u[1:2:2ng]; mod.dqg_sol .= u[2:2:2ng]
+    mod.dline_fl .= reshape(u[2ng+1:end], 8, nl)[1:4, :]
+    qp_check(qp_handle(mod), ccall((:ea_qp_get_line_array, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Int64),
+                                   qp_handle(mod), 0, mod.dline_var, 6nl)); return        # EA_QP_SQP_LINE, 6 x nline column-major
+end
+function admm_one_level(env::Env, mod::QpMod, device=nothing)       # the whole loop in one ccall
+    p = env.params
+    par = EaParams(p.mu_max, p.max_auglag, p.verbose, 0.0, p.inc_c, p.theta, p.outer_eps,
+                   p.MAX_MULTIPLIER, p.scale, p.obj_scale, p.outer_iterlim, 1)
+    info = EaInfo()
+    qp_check(qp_handle(mod), ccall((:ea_qp_admm_one_level, LIB), Cint, (Ptr{Cvoid}, Ref{EaParams}, Ref{EaInfo}),
+                                   qp_handle(mod), par, info))
+    i = mod.info
+    i.status = (:NotSpecified, :IterationLimit, :Solved)[info.status + 1]
+    i.inner, i.outer, i.cumul, i.objval, i.auglag = info.inner, info.outer, info.cumul, info.objval, info.auglag
+    i.primres, i.dualres, i.mismatch, i.time_overall = info.primres, info.dualres, info.mismatch, info.time_overall
+    p.initial_beta = 0; p.beta = 0; p.inner_iterlim = 1              # admm_one_level.jl:17-22
+    admm_poststep(env, mod, device)
+    return
+end
+
 end # module
