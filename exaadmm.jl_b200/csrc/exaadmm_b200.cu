@@ -52,6 +52,7 @@ struct ea_handle {
     Timers tm;
     int default_chunk = 16;
     int x_resident_blocks = 148;                // CTAs of k_xupdate resident on the device at once
+    unsigned *heavy_stamp_alloc = nullptr;      // d.heavy_stamp when heavy-first ordering is on
     // launch accounting / optional per-kernel timing of the fused loop
     double span_s = 0.0;                        // device time spent inside ea_run_inner* calls (events on h->stream)
     long long n_x = 0, n_bus = 0, n_other = 0;  // kernels launched
@@ -349,6 +350,18 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
         if ((rc = dev_upload(h, const_cast<int **>(&d.br_from), brf))) return bail(rc);
         if ((rc = dev_upload(h, const_cast<int **>(&d.br_to), brt))) return bail(rc);
         if ((rc = dev_alloc(h, &d.als, 3 * (size_t)nline))) return bail(rc);       // membuf rows 25-27 start at 0 (acopf_model.jl:87-88)
+        // heavy-first ordering of the branch kernel (kernels.cuh, Dev::heavy_stamp)
+        std::vector<int> slot_line(2 * (size_t)nline);
+        std::vector<double> slot_thresh(2 * (size_t)nline);
+        for (int l = 0; l < nline; ++l) {
+            slot_line[slot_from[l]] = l; slot_line[slot_to[l]] = l;
+            slot_thresh[slot_from[l]] = HEAVY_FRACTION * rate[l]; slot_thresh[slot_to[l]] = HEAVY_FRACTION * rate[l];
+        }
+        if ((rc = dev_upload(h, const_cast<int **>(&d.slot_line), slot_line))) return bail(rc);
+        if ((rc = dev_upload(h, const_cast<double **>(&d.slot_thresh), slot_thresh))) return bail(rc);
+        if ((rc = dev_alloc(h, &d.heavy_stamp, (size_t)nline))) return bail(rc);
+        h->heavy_stamp_alloc = d.heavy_stamp;
+        if ((rc = dev_alloc(h, &d.heavy_list[0], (size_t)nline)) || (rc = dev_alloc(h, &d.heavy_list[1], (size_t)nline))) return bail(rc);
     }
     {   // per generator slot
         auto permute = [&](const double *src) {
@@ -878,6 +891,11 @@ int ea_set_option(ea_handle_t *h, const char *name, double value) {
     if (!strcmp(name, "count_work")) { h->d.count_work = (int)value; return EA_OK; }   // 2: also phase timestamps
     if (!strcmp(name, "chunk")) { h->default_chunk = std::max(1, (int)value); return EA_OK; }
     if (!strcmp(name, "kernel_timing")) { h->kernel_timing = value != 0.0; return EA_OK; }
+    if (!strcmp(name, "heavy_first")) {             // 0: hand the branches out in index order (diagnostics)
+        if (value != 0.0 && !h->d.partitioned && !h->d.mp_sums) h->d.heavy_stamp = h->heavy_stamp_alloc;
+        else h->d.heavy_stamp = nullptr;
+        return EA_OK;
+    }
     return fail(h, EA_ERR_ARG, "ea_set_option: unknown option '%s'", name);
 }
 
@@ -930,6 +948,7 @@ int ea_set_partition(ea_handle_t *h, int32_t rank, int32_t nranks, int64_t n_own
         return fail(h, EA_ERR_ALLOC, "cudaMallocHost failed");
     d.gather = h->gather_dev;
     d.sendbuf = h->gather_dev + (size_t)rank * stride;
+    d.heavy_stamp = nullptr;                  // ghost ends get their z / lambda in k_finish, after the bus kernel
     d.partitioned = 1; d.rank = rank; d.nranks = nranks; d.n_ghost = (int)n_ghost; d.stride = stride;
     d.nbus_active = (int)n_owned_bus;
     if ((rc = build_bus_warps(h, hstart, (int)n_owned_bus))) return rc;
