@@ -5,7 +5,6 @@
 #include "kernels.cuh"
 #include "mp_kernels.cuh"
 #include "qp_kernels.cuh"
-#include "async.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -54,15 +53,6 @@ struct ea_handle {
     int default_chunk = 16;
     int x_resident_blocks = 148;                // CTAs of k_xupdate resident on the device at once
     unsigned *heavy_stamp_alloc = nullptr;      // d.heavy_stamp when heavy-first ordering is on
-    // dataflow inner loop (async.cuh)
-    int async_mode = 0;                         // option "async": ea_run_inner* runs the persistent dataflow kernel
-    bool async_ready = false;
-    AsyncDev ad{};
-    AsyncCtrl *actrl_host = nullptr;            // pinned
-    int async_grid = 0;
-    double async_bus_fraction = 0.25;           // share of the CTAs that work on buses
-    double async_budget_s = 5.0;                // a run that waits longer than this aborts instead of hanging
-    long long n_async = 0;                      // dataflow kernels launched
     // launch accounting / optional per-kernel timing of the fused loop
     double span_s = 0.0;                        // device time spent inside ea_run_inner* calls (events on h->stream)
     long long n_x = 0, n_bus = 0, n_other = 0;  // kernels launched
@@ -427,7 +417,6 @@ void ea_destroy(ea_handle_t *h) {
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
-    if (h->actrl_host) cudaFreeHost(h->actrl_host);
     if (h->res_host) cudaFreeHost(h->res_host);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &e : h->kev) if (e) cudaEventDestroy(e);
@@ -666,96 +655,6 @@ int ea_inner_iteration(ea_handle_t *h, int64_t inner, double beta, int32_t max_a
     return EA_OK;
 }
 
-// ---- dataflow path (async.cuh) ------------------------------------------------------------------------------------
-static int async_prepare(ea_handle *h) {
-    if (h->async_ready) return EA_OK;
-    int rc;
-    AsyncDev &a = h->ad;
-    const size_t nint = (size_t)h->nint, nl = (size_t)h->nline, nb = (size_t)h->nbus;
-    for (int k = 0; k < AD; ++k) {
-        if ((rc = dev_alloc(h, &a.u[k], nint)) || (rc = dev_alloc(h, &a.v[k], nint)) || (rc = dev_alloc(h, &a.z[k], nint)) ||
-            (rc = dev_alloc(h, &a.l[k], nint)) || (rc = dev_alloc(h, &a.als[k], 3 * nl)) || (rc = dev_alloc(h, &a.bsum[k], 4 * nb)))
-            return rc;
-    }
-    auto pow2 = [](size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; };
-    const size_t xcap = pow2(2 * nl + 131072), bcap = pow2(2 * nb + 131072);
-    if ((rc = dev_alloc(h, &a.xq, xcap)) || (rc = dev_alloc(h, &a.bq, bcap))) return rc;
-    a.xmask = (unsigned)(xcap - 1); a.bmask = (unsigned)(bcap - 1);
-    if ((rc = dev_alloc(h, &a.bus_cnt, nb)) || (rc = dev_alloc(h, &a.br_cnt, nl))) return rc;
-    if ((rc = dev_alloc(h, &a.c, 1))) return rc;
-    std::vector<int> hstart(nb + 1), iso;
-    CK(cudaMemcpy(hstart.data(), h->d.hstart, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost));
-    for (size_t b = 0; b < nb; ++b) if (hstart[b + 1] == hstart[b]) iso.push_back((int)b);
-    a.n_iso = (int)iso.size();
-    if (iso.empty()) iso.push_back(0);
-    if ((rc = dev_upload(h, const_cast<int **>(&a.iso_bus), iso))) return rc;
-    if (cudaMallocHost((void **)&h->actrl_host, sizeof(AsyncCtrl)) != cudaSuccess) return fail(h, EA_ERR_ALLOC, "cudaMallocHost failed");
-    int per_sm = 0, sms = 0;
-    if (cudaFuncSetAttribute(k_async, cudaFuncAttributeMaxDynamicSharedMemorySize, XTILE_BYTES) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_async, XBLOCK, XTILE_BYTES) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess || per_sm < 1)
-        return fail(h, EA_ERR_CUDA, "k_async occupancy query failed: %s", cudaGetErrorString(cudaGetLastError()));
-    h->async_grid = per_sm * sms;                 // every CTA must be resident: the workers wait on each other
-    if (h->async_grid < 3) return fail(h, EA_ERR_CUDA, "k_async: device too small for the dataflow kernel");
-    h->async_ready = true;
-    return EA_OK;
-}
-
-// One run of the inner loop (iterations inner_start+1 .. at most inner_limit) as one dataflow kernel.
-static int async_run(ea_handle *h, double beta, double eps_pri, int64_t inner_start, int64_t inner_limit, int32_t max_auglag,
-                     double mu_max, double scale, int64_t *inner_done, double out[4]) {
-    int rc = async_prepare(h);
-    if (rc) return rc;
-    AsyncDev &a = h->ad;
-    build_pow_table(h, mu_max);
-    const size_t vb = sizeof(double) * (size_t)h->nint;
-    // state of "iteration 0" -> ring slot 0
-    CK(cudaMemcpyAsync(a.u[0], h->d.u, vb, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(a.v[0], h->d.v, vb, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(a.l[0], h->d.l, vb, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(a.z[0], h->d.zbuf[h->zsel], vb, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(a.als[0], h->d.als, sizeof(double) * 3 * (size_t)h->nline, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemsetAsync(a.xq, 0, sizeof(unsigned long long) * ((size_t)a.xmask + 1), h->stream));
-    CK(cudaMemsetAsync(a.bq, 0, sizeof(unsigned long long) * ((size_t)a.bmask + 1), h->stream));
-    a.major0 = (long long)inner_start;
-    const int64_t steps = inner_limit - inner_start;
-    const int limit = (int)std::min<int64_t>(steps, 1 << 30);
-    const int nbw = std::max(2, std::min(h->async_grid - 1, 1 + (int)std::lround(h->async_bus_fraction * h->async_grid)));
-    a.nb = nbw;
-    k_async_begin<<<64, 256, 0, h->stream>>>(h->d, a, beta, eps_pri, limit, (unsigned long long)(h->async_budget_s * 1e9));
-    CK(cudaGetLastError());
-    k_async<<<h->async_grid, XBLOCK, XTILE_BYTES, h->stream>>>(h->d, a, h->pow_table, max_auglag, mu_max, scale);
-    CK(cudaGetLastError());
-    h->n_other++; h->n_async++;
-    CK(cudaMemcpyAsync(h->actrl_host, a.c, sizeof(AsyncCtrl), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    const AsyncCtrl &c = *h->actrl_host;
-    if (c.halt != 1)
-        return fail(h, EA_ERR_STATE, "dataflow kernel gave up after %.1f s (tested %d, x %llu, bus %llu tasks)", h->async_budget_s,
-                    c.tested, c.n_x, c.n_b);
-    if (h->d.count_work > 1) {
-        const int nxw = (h->async_grid - a.nb) * (XBLOCK / 32), nbw2 = (a.nb - 1) * (XBLOCK / 32);
-        const double sx = 1.0 / std::max(1, nxw), sb = 1.0 / std::max(1, nbw2);
-        fprintf(stderr, "[async] %d iterations; per branch-worker warp (Mcycles): refill %.2f eval %.2f completion %.2f compute %.2f "
-                        "idle %.2f, rounds %.0f | per bus-worker warp: poll %.2f task %.2f arrivals %.2f idle %.2f, batches %.0f, "
-                        "lanes/batch %.1f | tasks x %llu bus %llu\n",
-                c.stop_iter, 1e-6 * c.diag[0] * sx, 1e-6 * c.diag[1] * sx, 1e-6 * c.diag[2] * sx, 1e-6 * c.diag[3] * sx,
-                1e-6 * c.diag[4] * sx, c.diag[5] * sx, 1e-6 * c.diag[8] * sb, 1e-6 * c.diag[9] * sb, 1e-6 * c.diag[10] * sb,
-                1e-6 * c.diag[11] * sb, c.diag[12] * sb, c.diag[12] ? (double)c.diag[13] / (double)c.diag[12] : 0.0, c.n_x, c.n_b);
-    }
-    const int K = c.stop_iter, s1 = K % AD, s0 = (K - 1) % AD;
-    // iteration K is the state; z of K-1 is z_prev
-    CK(cudaMemcpyAsync(h->d.u, a.u[s1], vb, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d.v, a.v[s1], vb, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d.l, a.l[s1], vb, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d.zbuf[h->zsel], a.z[s1], vb, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d.zbuf[h->zsel ^ 1], a.z[s0], vb, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d.als, a.als[s1], sizeof(double) * 3 * (size_t)h->nline, cudaMemcpyDeviceToDevice, h->stream));
-    *inner_done = inner_start + K;
-    for (int k = 0; k < 4; ++k) out[k] = c.res[k];
-    return EA_OK;
-}
-
 int ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_start, int64_t inner_limit,
                       int32_t max_auglag, double mu_max, double scale, int32_t chunk, int64_t *inner_done, double out[4]) {
     if (!h || !inner_done || !out) return EA_ERR_ARG;
@@ -765,17 +664,6 @@ int ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_
     const double eps_pri = std::sqrt((double)h->nvar_global) / (2500.0 * (double)outer);    // admm_two_level.jl:45
     if (inner_limit == inner_start) { *inner_done = inner_start; for (int k = 0; k < 4; ++k) out[k] = 0.0; return EA_OK; }
     CK(cudaEventRecord(h->span0, h->stream));
-    if (h->async_mode && !h->d.partitioned && !h->d.mp_sums && h->nline > 0) {
-        int rc = async_run(h, beta, eps_pri, inner_start, inner_limit, max_auglag, mu_max, scale, inner_done, out);
-        if (rc) return rc;
-        // keep the device control block of the synchronous path in step (inner count, z selector unchanged)
-        if ((rc = sync_ctrl_to_device(h, beta, eps_pri, *inner_done, inner_limit))) return rc;
-        if ((rc = residual_vectors(h, nullptr))) return rc;
-        CK(cudaEventRecord(h->span1, h->stream));
-        CK(cudaEventSynchronize(h->span1));
-        h->span_s += elapsed_s(h->span0, h->span1);
-        return EA_OK;
-    }
     int rc = sync_ctrl_to_device(h, beta, eps_pri, inner_start, inner_limit);
     if (rc) return rc;
     int64_t enq = inner_start;
@@ -1003,9 +891,6 @@ int ea_set_option(ea_handle_t *h, const char *name, double value) {
     if (!strcmp(name, "count_work")) { h->d.count_work = (int)value; return EA_OK; }   // 2: also phase timestamps
     if (!strcmp(name, "chunk")) { h->default_chunk = std::max(1, (int)value); return EA_OK; }
     if (!strcmp(name, "kernel_timing")) { h->kernel_timing = value != 0.0; return EA_OK; }
-    if (!strcmp(name, "async")) { h->async_mode = value != 0.0; return EA_OK; }
-    if (!strcmp(name, "async_bus_fraction")) { h->async_bus_fraction = std::min(0.9, std::max(0.02, value)); return EA_OK; }
-    if (!strcmp(name, "async_budget_s")) { h->async_budget_s = std::max(0.01, value); return EA_OK; }
     if (!strcmp(name, "heavy_first")) {             // 0: hand the branches out in index order (diagnostics)
         if (value != 0.0 && !h->d.partitioned && !h->d.mp_sums) h->d.heavy_stamp = h->heavy_stamp_alloc;
         else h->d.heavy_stamp = nullptr;

@@ -26,16 +26,11 @@ assert lib.ea_init_solution(h, rho_pq, rho_va) == 0
 lib.ea_set_option(h, b"chunk", float(chunk))
 import os
 lib.ea_set_option(h, b"heavy_first", float(os.environ.get("EA_HEAVY_FIRST", "1")))
-lib.ea_set_option(h, b"async", float(os.environ.get("EA_ASYNC", "0")))
-if "EA_ASYNC_BUS" in os.environ:
-    lib.ea_set_option(h, b"async_bus_fraction", float(os.environ["EA_ASYNC_BUS"]))
 res = np.zeros(4); got = C.c_int64(); nz = C.c_double()
 lib.ea_outer_prestep(h, C.byref(nz))
 # eps_pri is never met with outer = huge -> run exactly the requested number of iterations
 lib.ea_run_inner_from(h, 10**9, par.initial_beta, 0, W, par.max_auglag, par.mu_max, par.scale, chunk, C.byref(got), dptr(res))
 lib.ea_reset_counters(h)
-if os.environ.get("EA_ASYNC_PROF"):
-    lib.ea_set_option(h, b"count_work", 2.0)
 lib.ea_set_option(h, b"kernel_timing", 1.0)
 t = time.perf_counter()
 lib.ea_run_inner_from(h, 10**9, par.initial_beta, W, W + K, par.max_auglag, par.mu_max, par.scale, chunk, C.byref(got), dptr(res))
