@@ -52,7 +52,6 @@ struct ea_handle {
     Timers tm;
     int default_chunk = 16;
     int x_resident_blocks = 148;                // CTAs of k_xupdate resident on the device at once
-    unsigned *heavy_stamp_alloc = nullptr;      // d.heavy_stamp when heavy-first ordering is on
     // launch accounting / optional per-kernel timing of the fused loop
     double span_s = 0.0;                        // device time spent inside ea_run_inner* calls (events on h->stream)
     long long n_x = 0, n_bus = 0, n_other = 0;  // kernels launched
@@ -183,7 +182,8 @@ int launch_x(ea_handle *h, long long major, int zsel, int max_auglag, double mu_
     if (major > 0 && lines)     // step-wise call: the fused loop resets the work queue itself (k_bus / k_ctrl_begin)
         CK(cudaMemsetAsync(&h->d.ctrl->next_line, 0, sizeof(int), stream));
     // persistent grid: as many CTAs as are resident at once, capped by the work available
-    const int64_t work_blocks = std::max<int64_t>((h->nline + XBLOCK - 1) / XBLOCK, (h->ngen + XBLOCK - 1) / XBLOCK);
+    // one lane per branch at least: small grids are spread over all resident warps (k_xupdate: lanes_on)
+    const int64_t work_blocks = std::max<int64_t>((h->nline + XBLOCK / 32 - 1) / (XBLOCK / 32), (h->ngen + XBLOCK - 1) / XBLOCK);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->x_resident_blocks, work_blocks));
     k_xupdate<<<grid, XBLOCK, XTILE_BYTES, stream>>>(h->d, h->pow_table, major, zsel, max_auglag, mu_max, scale, lines, gens);
     CK(cudaGetLastError());
@@ -243,6 +243,14 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
 
     h = new ea_handle();
     auto bail = [&](int rc) { g_create_error = h->err; ea_destroy(h); return rc; };
+    const bool prof_create = getenv("EXAADMM_PROFILE_CREATE") != nullptr;
+    auto lap_t = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!prof_create) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ea_create] %-28s %8.3f ms\n", what, 1e3 * std::chrono::duration<double>(now - lap_t).count());
+        lap_t = now;
+    };
     h->device = device;
     if (cudaSetDevice(device) != cudaSuccess) return bail(fail(h, EA_ERR_CUDA, "cudaSetDevice(%d) failed", device));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -265,6 +273,7 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
             return bail(fail(h, EA_ERR_CUDA, "k_xupdate occupancy query failed: %s", cudaGetErrorString(cudaGetLastError())));
         h->x_resident_blocks = per_sm * sms;
     }
+    lap("stream, events, occupancy");
     const int ngen = (int)G->ngen, nline = (int)G->nline, nbus = (int)G->nbus;
     h->ngen = ngen; h->nline = nline; h->nbus = nbus; h->nvar = 2 * (int64_t)ngen + 8 * (int64_t)nline;
     const int gpad = ((2 * ngen + 3) / 4) * 4;
@@ -311,6 +320,7 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
         ref2int[base + 4] = f + 2; ref2int[base + 5] = t + 2; ref2int[base + 6] = f + 3; ref2int[base + 7] = t + 3;
     }
 
+    lap("layout (host)");
     // ---- device allocations -------------------------------------------------------------
     int rc;
     Dev &d = h->d;
@@ -322,6 +332,7 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     d.rp = h->fields[EA_RP]; d.rd = h->fields[EA_RD]; d.axby = h->fields[EA_AX_PLUS_BY];
     h->zsel = 0;
 
+    lap("state vectors (alloc + memset)");
     if ((rc = dev_upload(h, const_cast<int **>(&d.slot_from), slot_from))) return bail(rc);
     if ((rc = dev_upload(h, const_cast<int **>(&d.slot_to), slot_to))) return bail(rc);
     if ((rc = dev_upload(h, const_cast<int **>(&d.hstart), hstart))) return bail(rc);
@@ -329,6 +340,7 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     if ((rc = dev_upload(h, &h->ref2int, ref2int))) return bail(rc);
     if ((rc = build_bus_warps(h, hstart, nbus))) return bail(rc);
 
+    lap("index maps + bus warps");
     {   // per line
         std::vector<double> Y(8 * (size_t)nline), xlu(8 * (size_t)nline), rate(nline);
         std::vector<int> brf(nline), brt(nline);
@@ -350,19 +362,8 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
         if ((rc = dev_upload(h, const_cast<int **>(&d.br_from), brf))) return bail(rc);
         if ((rc = dev_upload(h, const_cast<int **>(&d.br_to), brt))) return bail(rc);
         if ((rc = dev_alloc(h, &d.als, 3 * (size_t)nline))) return bail(rc);       // membuf rows 25-27 start at 0 (acopf_model.jl:87-88)
-        // heavy-first ordering of the branch kernel (kernels.cuh, Dev::heavy_stamp)
-        std::vector<int> slot_line(2 * (size_t)nline);
-        std::vector<double> slot_thresh(2 * (size_t)nline);
-        for (int l = 0; l < nline; ++l) {
-            slot_line[slot_from[l]] = l; slot_line[slot_to[l]] = l;
-            slot_thresh[slot_from[l]] = HEAVY_FRACTION * rate[l]; slot_thresh[slot_to[l]] = HEAVY_FRACTION * rate[l];
-        }
-        if ((rc = dev_upload(h, const_cast<int **>(&d.slot_line), slot_line))) return bail(rc);
-        if ((rc = dev_upload(h, const_cast<double **>(&d.slot_thresh), slot_thresh))) return bail(rc);
-        if ((rc = dev_alloc(h, &d.heavy_stamp, (size_t)nline))) return bail(rc);
-        h->heavy_stamp_alloc = d.heavy_stamp;
-        if ((rc = dev_alloc(h, &d.heavy_list[0], (size_t)nline)) || (rc = dev_alloc(h, &d.heavy_list[1], (size_t)nline))) return bail(rc);
     }
+    lap("per-line data");
     {   // per generator slot
         auto permute = [&](const double *src) {
             std::vector<double> v(ngen);
@@ -389,6 +390,7 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
         if ((rc = dev_upload(h, const_cast<double **>(&d.Vmin), std::vector<double>(G->Vmin, G->Vmin + nbus)))) return bail(rc);
         if ((rc = dev_upload(h, const_cast<double **>(&d.Vmax), std::vector<double>(G->Vmax, G->Vmax + nbus)))) return bail(rc);
     }
+    lap("per-generator / per-bus data");
     h->max_blocks = std::max(nblocks((int64_t)2 * nline + 32 * (int64_t)nbus, BBLOCK), 1024);
     if ((rc = dev_alloc(h, &d.partials, 4 * (size_t)h->max_blocks))) return bail(rc);
     if ((rc = dev_alloc(h, &d.ctrl, 1))) return bail(rc);
@@ -399,9 +401,15 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     d.nbus_active = nbus;
     h->n_owned_entries = nint;
     h->nvar_global = h->nvar;
-    if (cudaMallocHost((void **)&h->ctrl_host, sizeof(Ctrl)) != cudaSuccess) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
-    if (cudaMallocHost((void **)&h->res_host, 4 * sizeof(double)) != cudaSuccess) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
+    {   // one pinned block for the control-block mirror and the 4 norms (a pinned allocation costs ~1.3 ms)
+        static_assert(sizeof(Ctrl) % sizeof(double) == 0, "res_host follows ctrl_host in one pinned block");
+        void *pin = nullptr;
+        if (cudaMallocHost(&pin, sizeof(Ctrl) + 4 * sizeof(double)) != cudaSuccess) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
+        h->ctrl_host = static_cast<Ctrl *>(pin);
+        h->res_host = reinterpret_cast<double *>(static_cast<char *>(pin) + sizeof(Ctrl));
+    }
     memset(h->ctrl_host, 0, sizeof(Ctrl));
+    lap("control blocks, pinned memory");
     *out = h;
     return EA_OK;
 }
@@ -416,8 +424,7 @@ void ea_destroy(ea_handle_t *h) {
     if (h->gather_host) cudaFreeHost(h->gather_host);
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
-    if (h->res_host) cudaFreeHost(h->res_host);
+    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);       // res_host lives in the same pinned block
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &e : h->kev) if (e) cudaEventDestroy(e);
     if (h->span0) cudaEventDestroy(h->span0);
@@ -891,11 +898,6 @@ int ea_set_option(ea_handle_t *h, const char *name, double value) {
     if (!strcmp(name, "count_work")) { h->d.count_work = (int)value; return EA_OK; }   // 2: also phase timestamps
     if (!strcmp(name, "chunk")) { h->default_chunk = std::max(1, (int)value); return EA_OK; }
     if (!strcmp(name, "kernel_timing")) { h->kernel_timing = value != 0.0; return EA_OK; }
-    if (!strcmp(name, "heavy_first")) {             // 0: hand the branches out in index order (diagnostics)
-        if (value != 0.0 && !h->d.partitioned && !h->d.mp_sums) h->d.heavy_stamp = h->heavy_stamp_alloc;
-        else h->d.heavy_stamp = nullptr;
-        return EA_OK;
-    }
     return fail(h, EA_ERR_ARG, "ea_set_option: unknown option '%s'", name);
 }
 
@@ -948,7 +950,6 @@ int ea_set_partition(ea_handle_t *h, int32_t rank, int32_t nranks, int64_t n_own
         return fail(h, EA_ERR_ALLOC, "cudaMallocHost failed");
     d.gather = h->gather_dev;
     d.sendbuf = h->gather_dev + (size_t)rank * stride;
-    d.heavy_stamp = nullptr;                  // ghost ends get their z / lambda in k_finish, after the bus kernel
     d.partitioned = 1; d.rank = rank; d.nranks = nranks; d.n_ghost = (int)n_ghost; d.stride = stride;
     d.nbus_active = (int)n_owned_bus;
     if ((rc = build_bus_warps(h, hstart, (int)n_owned_bus))) return rc;

@@ -30,10 +30,6 @@ struct Ctrl {                 // device-resident loop control (one per handle)
     unsigned ticket;          // last-block election for the residual reduction
     int next_line;            // work queue head of the branch kernel (reset for the next x-update)
     unsigned long long seq;   // partitioned iterations executed since the handle was created (exchange stamps / parity)
-    // heavy-first ordering of the branch kernel (see Dev::heavy_stamp): stamp of the NEXT x-update and the number of
-    // branches the bus kernel has flagged for it (double-buffered by the stamp's parity)
-    unsigned xseq;
-    int heavy_n[2];
 };
 
 struct Counters { unsigned long long v[8]; unsigned long long t[4]; };   // t: first start, queue empty, last end (globaltimer ns), launches
@@ -83,18 +79,8 @@ struct Dev {                  // everything the kernels need, passed by value
     // over instead of finishing the iteration itself (k_mp_finish does, for all periods at once).
     const double *rn_u, *rn_l, *rn_rho, *rn_z[2];
     double *mp_sums;
-    // heavy-first ordering (fused single-handle loop only; null otherwise). The kernel lasts as long as its slowest
-    // branch: a branch whose line limit becomes active runs ~25 TRON solves in a row (penalty ladder), ~20x the mean.
-    // Such branches are recognisable BEFORE the x-update: the flow the consensus terms ask for, xbar - z - lambda/rho,
-    // is at or beyond the limit. The fused bus kernel computes exactly these quantities per branch end, so it flags
-    // the branch (stamp + list), and the branch kernel hands out the flagged branches first: the long chains start at
-    // t = 0 instead of somewhere inside the bulk. Results do not depend on the order (branches are independent).
-    unsigned *heavy_stamp;                // nline: stamp of the last x-update the branch was flagged for
-    int *heavy_list[2];                   // nline each
-    const int *slot_line;                 // 2 nline: branch of each end slot
-    const double *slot_thresh;            // 2 nline: HEAVY_FRACTION * rateA of that branch
 };
-constexpr double HEAVY_FRACTION = 0.9;
+
 
 __device__ __forceinline__ double *xseg(const Dev &d, double *base, int parity, int r) {
     return base + ((size_t)parity * d.nranks + r) * d.stride;
@@ -313,19 +299,6 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
     if (do_gens)
         for (int k = blockIdx.x * XBLOCK + threadIdx.x; k < d.ngen; k += gridDim.x * XBLOCK) generator_update(d, z, k);
     if (!do_lines) return;
-    // heavy-first: queue positions [0, nheavy) are the branches the bus kernel flagged, the rest are all branches in
-    // order, skipping the flagged ones
-    unsigned stamp = 0u;
-    int nheavy = 0;
-    const int *heavy = nullptr;
-    if (major_arg == 0 && d.heavy_stamp) {
-        stamp = d.ctrl->xseq;
-        nheavy = d.ctrl->heavy_n[stamp & 1u];
-        heavy = d.heavy_list[stamp & 1u];
-        if (blockIdx.x == 0 && threadIdx.x == 0) d.ctrl->heavy_n[(stamp & 1u) ^ 1u] = 0;    // the next bus kernel fills this one
-    }
-    const int nqueue = d.nline + nheavy;
-
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     unsigned long long t_now = 0;
@@ -337,7 +310,11 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
     double *col = tile + threadIdx.x;
     const branch::Objective<branch::TileView<XBLOCK>> eval{ { col }, scale };
     branch::Lane L;
-    L.phase = branch::NEED;
+    // Small grids: fewer lanes per warp, more warps. A round of the state machine costs a warp ~14 us when its 32 lanes
+    // sit in different phases of different branches, ~7.5 us when only a few lanes are live; with fewer branches than
+    // resident lanes the work is spread over all warps instead of filling the first ones.
+    const int lanes_on = min(32, max(1, (d.nline + gridDim.x * (XBLOCK / 32) - 1) / (gridDim.x * (XBLOCK / 32))));
+    L.phase = (lane < lanes_on) ? branch::NEED : branch::DONE;
     L.step_pending = false;
     int I = -1;
     unsigned long long work[7] = { 0, 0, 0, 0, 0, 0, 0 };  // calls, auglag, evals, cg, shifts, rejected, hit_max
@@ -355,12 +332,8 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
                 if (lane == __ffs(m) - 1) base = atomicAdd(&d.ctrl->next_line, __popc(m));
                 base = __shfl_sync(full, base, __ffs(m) - 1);
                 if (need) {
-                    const int pos = base + __popc(m & ((1u << lane) - 1u));
-                    bool skip = false;
-                    if (pos < nheavy) I = heavy[pos];
-                    else { I = pos - nheavy; skip = nheavy > 0 && I < d.nline && d.heavy_stamp[I] == stamp; }
-                    if (skip) { /* already handed out from the list: ask again in the next pass */ }
-                    else if (pos < nqueue) { load_branch(d, z, I, major, col, L); branch::begin(L, T); }
+                    I = base + __popc(m & ((1u << lane) - 1u));
+                    if (I < d.nline) { load_branch(d, z, I, major, col, L); branch::begin(L, T); }
                     else {
                         L.phase = branch::DONE;
                         if (d.count_work > 1 && !saw_empty) {
@@ -537,15 +510,6 @@ __device__ __forceinline__ void bus_end_scatter(const Dev &d, double *znew, int 
         ln.t = l_update(lz.t, beta, zn.t);
         st4(znew + d.gpad, s, zn);
         st4(d.l + d.gpad, s, ln);
-        if (d.heavy_stamp) {               // will the next x-update of this branch run into its line limit?
-            const double tp = (v.p - zn.p) - ln.p * irp, tq = (v.q - zn.q) - ln.q * irq;
-            if (tp * tp + tq * tq > d.slot_thresh[s]) {
-                const unsigned stamp = d.ctrl->xseq + 1u;
-                const int I = d.slot_line[s];
-                if (atomicExch(&d.heavy_stamp[I], stamp) != stamp)        // the other end may have flagged it already
-                    d.heavy_list[stamp & 1u][atomicAdd(&d.ctrl->heavy_n[stamp & 1u], 1)] = I;
-            }
-        }
         const double uu[4] = { u.p, u.q, u.w, u.t }, vv[4] = { v.p, v.q, v.w, v.t };
         const double zz[4] = { zn.p, zn.q, zn.w, zn.t }, zo[4] = { z.p, z.q, z.w, z.t };
 #pragma unroll
@@ -687,7 +651,6 @@ __device__ __forceinline__ void bus_body(const Dev &d, int zsel_arg, double beta
             c->inner = inner;
             c->zsel = zsel ^ 1;
             c->next_line = 0;
-            c->xseq += 1u;
             // admm_two_level.jl:60-62 and the `while inner < inner_iterlim` bound (:34)
             if (c->res[0] <= c->eps_pri || inner >= c->inner_limit) c->done = 1;
         }
@@ -843,7 +806,6 @@ __global__ void k_membuf_row(Dev d, int zsel, int row, double *out) {
 __global__ void k_ctrl_begin(Ctrl *c, double beta, double eps_pri, long long inner0, long long inner_limit, int zsel) {
     c->beta = beta; c->eps_pri = eps_pri; c->inner = inner0; c->inner_limit = inner_limit;
     c->done = 0; c->zsel = zsel; c->ticket = 0u; c->next_line = 0;
-    c->xseq += 1u; c->heavy_n[0] = 0; c->heavy_n[1] = 0;      // flags raised for an x-update that never ran are void
 }
 
 // diagnostics: evaluate f, g, H for a batch of points (unit parity vs the oracle)

@@ -387,9 +387,7 @@ int  ea_get_counters(ea_handle_t *h, ea_counters_t *out);
 int  ea_reset_counters(ea_handle_t *h);
 /* Options: "count_work" (0/1, atomics for ea_counters_t in the branch kernel, default 1),
  * "chunk" (inner iterations enqueued per host poll in ea_run_inner*, default 16),
- * "kernel_timing" (0/1, bracket every kernel of the fused loop with CUDA events),
- * "heavy_first" (0/1, default 1: the fused loop hands out first the branches whose line limit is about to become
- * active - the long augmented-Lagrangian chains - so that they do not start late; results do not depend on it). */
+ * "kernel_timing" (0/1, bracket every kernel of the fused loop with CUDA events). */
 int  ea_set_option(ea_handle_t *h, const char *name, double value);
 /* Launch accounting since the last ea_reset_counters: out = { device seconds spent in
  * ea_run_inner* (events on the library's stream), x-update launches, their summed

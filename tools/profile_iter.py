@@ -25,7 +25,6 @@ assert lib.ea_create(C.byref(gs), 0, C.byref(h)) == 0, lib.ea_last_error(None)
 assert lib.ea_init_solution(h, rho_pq, rho_va) == 0
 lib.ea_set_option(h, b"chunk", float(chunk))
 import os
-lib.ea_set_option(h, b"heavy_first", float(os.environ.get("EA_HEAVY_FIRST", "1")))
 res = np.zeros(4); got = C.c_int64(); nz = C.c_double()
 lib.ea_outer_prestep(h, C.byref(nz))
 # eps_pri is never met with outer = huge -> run exactly the requested number of iterations
