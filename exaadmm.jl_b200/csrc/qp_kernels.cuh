@@ -97,7 +97,13 @@ k_qp_xupdate(Dev d, QpDev q, branch::PowTable T, long long major_arg, int zsel, 
     unsigned long long work[3] = { 0, 0, 0 };
     int mx = 0;
     qpsub::TileStore<QBLOCK> st{ tile + threadIdx.x };
-    for (int I = tid; I < nl; I += nthr) {
+    // A warp runs as long as its slowest lane (a branch with binding limits: tens of TRON solves) and pays for every
+    // path its lanes take; with fewer branches than resident lanes the branches are spread over all warps, a few lanes
+    // each (2869-like grid, 4582 branches: 4 lanes per warp on 1184 warps instead of 32 lanes on 144).
+    const int nwarps = gridDim.x * (QBLOCK / 32), lane = threadIdx.x & 31, gwarp = tid >> 5;
+    const int lanes_on = min(32, max(1, (nl + nwarps - 1) / nwarps));
+    if (lane >= lanes_on) return;
+    for (int I = gwarp * lanes_on + lane; I < nl; I += nwarps * lanes_on) {
         qpsub::Inputs in;
         const int sf = d.slot_from[I], sto = d.slot_to[I];
         {
@@ -146,19 +152,10 @@ k_qp_xupdate(Dev d, QpDev q, branch::PowTable T, long long major_arg, int zsel, 
         work[0] += 1; work[1] += (unsigned)R.it; work[2] += (unsigned)R.evals;
         mx = max(mx, R.it);
     }
-    if (d.count_work) {
-        const unsigned full = 0xffffffffu;
+    if (d.count_work && work[0]) {          // (lanes beyond lanes_on have left: no warp-wide shuffles here)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) work[k] += __shfl_down_sync(full, work[k], o);
-            mx = max(mx, __shfl_down_sync(full, mx, o));
-        }
-        if ((threadIdx.x & 31) == 0 && work[0]) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) atomicAdd(&q.counters[k], work[k]);
-            atomicMax(&q.counters[3], (unsigned long long)mx);
-        }
+        for (int k = 0; k < 3; ++k) atomicAdd(&q.counters[k], work[k]);
+        atomicMax(&q.counters[3], (unsigned long long)mx);
     }
 }
 
