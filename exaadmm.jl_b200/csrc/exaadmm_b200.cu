@@ -51,6 +51,12 @@ struct ea_handle {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     Timers tm;
     int default_chunk = 16;
+    // the chunk of the fused loop as a CUDA graph (every kernel argument is constant: what changes lives in ctrl)
+    int use_graph = 1;
+    cudaGraphExec_t graph = nullptr;
+    int graph_chunk = 0, graph_max_auglag = 0, graph_count_work = 0;
+    double graph_mu_max = 0.0, graph_scale = 0.0;
+    long long n_replay = 0;
     int x_resident_blocks = 148;                // CTAs of k_xupdate resident on the device at once
     // launch accounting / optional per-kernel timing of the fused loop
     double span_s = 0.0;                        // device time spent inside ea_run_inner* calls (events on h->stream)
@@ -212,6 +218,10 @@ int build_bus_warps(ea_handle *h, const std::vector<int> &hstart, int nbus_activ
     if (!cur.empty()) flush(cur);
     h->d.n_bus_warps = (int)(info.size() / 32);
     return dev_upload(h, const_cast<int4 **>(&h->d.lane_info), info);
+}
+
+void drop_loop_graph(ea_handle *h) {
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
 }
 
 double elapsed_s(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return 1e-3 * ms; }
@@ -418,6 +428,7 @@ void ea_destroy(ea_handle_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_loop_graph(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void *p : h->peer_maps) if (p) cudaIpcCloseMemHandle(p);
     if (h->xbuf) cudaFree(h->xbuf);
@@ -662,6 +673,31 @@ int ea_inner_iteration(ea_handle_t *h, int64_t inner, double beta, int32_t max_a
     return EA_OK;
 }
 
+// `chunk` iterations of the fused loop (2 launches each) captured once and replayed: launch-bound grids (a few thousand
+// branches) spend a third of the iteration between kernels otherwise. Launches after the loop has finished are no-ops
+// on the device (ctrl->done), so a replay may overshoot the iteration limit.
+static int build_loop_graph(ea_handle *h, int chunk, int max_auglag, double mu_max, double scale) {
+    if (h->graph && h->graph_chunk == chunk && h->graph_max_auglag == max_auglag && h->graph_mu_max == mu_max &&
+        h->graph_scale == scale && h->graph_count_work == h->d.count_work) return EA_OK;
+    drop_loop_graph(h);
+    build_pow_table(h, mu_max);
+    const long long n_x = h->n_x, n_bus = h->n_bus, n_other = h->n_other;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = EA_OK;
+    for (int i = 0; i < chunk && rc == EA_OK; ++i) rc = enqueue_iteration(h, max_auglag, mu_max, scale, i);
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    h->n_x = n_x; h->n_bus = n_bus; h->n_other = n_other;             // counted per replay instead
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(h, EA_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    const cudaError_t e2 = cudaGraphInstantiate(&h->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) { h->graph = nullptr; return fail(h, EA_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e2)); }
+    h->graph_chunk = chunk; h->graph_max_auglag = max_auglag; h->graph_mu_max = mu_max; h->graph_scale = scale;
+    h->graph_count_work = h->d.count_work;
+    return EA_OK;
+}
+
 int ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_start, int64_t inner_limit,
                       int32_t max_auglag, double mu_max, double scale, int32_t chunk, int64_t *inner_done, double out[4]) {
     if (!h || !inner_done || !out) return EA_ERR_ARG;
@@ -674,10 +710,17 @@ int ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_
     int rc = sync_ctrl_to_device(h, beta, eps_pri, inner_start, inner_limit);
     if (rc) return rc;
     int64_t enq = inner_start;
+    const bool graph = h->use_graph && !h->kernel_timing && !h->d.partitioned && chunk > 1 && inner_limit - inner_start >= chunk;
+    if (graph && (rc = build_loop_graph(h, chunk, max_auglag, mu_max, scale))) return rc;
     for (;;) {
-        const int64_t todo = std::min<int64_t>(chunk, inner_limit - enq);
-        for (int64_t i = 0; i < todo; ++i)
-            if ((rc = enqueue_iteration(h, max_auglag, mu_max, scale, (int)i))) return rc;
+        const int64_t todo = graph ? chunk : std::min<int64_t>(chunk, inner_limit - enq);
+        if (graph) {
+            CK(cudaGraphLaunch(h->graph, h->stream));
+            h->n_replay++; h->n_x += chunk; h->n_bus += chunk;
+        } else {
+            for (int64_t i = 0; i < todo; ++i)
+                if ((rc = enqueue_iteration(h, max_auglag, mu_max, scale, (int)i))) return rc;
+        }
         enq += todo;
         if ((rc = fetch_ctrl(h))) return rc;
         if (h->kernel_timing) {
@@ -898,6 +941,7 @@ int ea_set_option(ea_handle_t *h, const char *name, double value) {
     if (!strcmp(name, "count_work")) { h->d.count_work = (int)value; return EA_OK; }   // 2: also phase timestamps
     if (!strcmp(name, "chunk")) { h->default_chunk = std::max(1, (int)value); return EA_OK; }
     if (!strcmp(name, "kernel_timing")) { h->kernel_timing = value != 0.0; return EA_OK; }
+    if (!strcmp(name, "use_graph")) { h->use_graph = value != 0.0; return EA_OK; }
     return fail(h, EA_ERR_ARG, "ea_set_option: unknown option '%s'", name);
 }
 

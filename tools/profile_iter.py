@@ -25,12 +25,13 @@ assert lib.ea_create(C.byref(gs), 0, C.byref(h)) == 0, lib.ea_last_error(None)
 assert lib.ea_init_solution(h, rho_pq, rho_va) == 0
 lib.ea_set_option(h, b"chunk", float(chunk))
 import os
+lib.ea_set_option(h, b"use_graph", float(os.environ.get("EA_USE_GRAPH", "1")))
 res = np.zeros(4); got = C.c_int64(); nz = C.c_double()
 lib.ea_outer_prestep(h, C.byref(nz))
 # eps_pri is never met with outer = huge -> run exactly the requested number of iterations
 lib.ea_run_inner_from(h, 10**9, par.initial_beta, 0, W, par.max_auglag, par.mu_max, par.scale, chunk, C.byref(got), dptr(res))
 lib.ea_reset_counters(h)
-lib.ea_set_option(h, b"kernel_timing", 1.0)
+lib.ea_set_option(h, b"kernel_timing", float(os.environ.get("EA_KERNEL_TIMING", "1")))
 t = time.perf_counter()
 lib.ea_run_inner_from(h, 10**9, par.initial_beta, W, W + K, par.max_auglag, par.mu_max, par.scale, chunk, C.byref(got), dptr(res))
 dt = time.perf_counter() - t
