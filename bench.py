@@ -85,48 +85,74 @@ def default_params(workload):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 5 ms from a thread (a query costs well
+    under a millisecond; `nvidia-smi -lms` needs ~100 ms to produce its first line, longer than a short timed region),
+    plus one sample at the moment the region ends. Falls back to one nvidia-smi query if NVML is unavailable."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index=0):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.nvml = None
+        self.hd = None
+        self.sm, self.reasons, self.mx = [], set(), None
+        self.running = False
+        self.thread = None
+
+    def _sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.hd, n.NVML_CLOCK_SM)))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.hd))
+        except Exception:
+            mask = 0
+        for name, bit in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while self.running:
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.005)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.hd = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.hd, pynvml.NVML_CLOCK_SM))
+            self.running = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.nvml = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            p = [t.strip() for t in ln.split(",")]
-            if len(p) < 7:
-                continue
+        if self.nvml is not None:
             try:
-                sm.append(float(p[0])); mx.append(float(p[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self._sample()                      # the region has just ended: still at its clocks
+            except Exception:
+                pass
+            self.running = False
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 5 ms period"}
+        try:                                        # no NVML binding: one nvidia-smi query right after the region
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            p = [t.strip() for t in out]
+            reasons = [n for (n, _), v in zip(self.REASONS, p[2:6]) if v.lower().startswith("active")]
+            return {"sm_mhz": float(p[0]), "sm_max_mhz": float(p[1]), "reasons": sorted(reasons), "samples": 1,
+                    "source": "nvidia-smi, one query at the end of the region"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"], "samples": 0}
 
 
 # ---------------------------------------------------------------------------------------
