@@ -207,6 +207,28 @@ def test_run_inner_stops_on_the_same_iteration_as_the_host_loop():
     np.testing.assert_array_equal(counts[0][4], counts[2][4])
 
 
+@pytest.mark.parametrize("chunk", [16, 5])
+def test_graph_replay_equals_plain_launches(chunk):
+    """The fused loop replayed from a CUDA graph (default) and enqueued launch by launch: same stopping iteration, same
+    state bit for bit - on a small grid whose branches are spread over all warps (a few live lanes per warp) and with
+    a chunk size that does not divide the iteration count."""
+    d = synthetic_case(300, 40, 420, seed=301)
+    outs = []
+    for graph in (1, 0):
+        env = AdmmEnv(d, 4e2, 4e4, use_gpu=True, verbose=0)
+        mod = ModelAcopf(env)
+        mod.set_option("use_graph", graph)
+        mod.set_option("chunk", chunk)
+        env.params.outer_iterlim = 3; env.params.inner_iterlim = 400
+        admm_two_level(env, mod, None, mode="native")
+        outs.append((mod.info.outer, mod.info.cumul, mod.info.inner, mod.info.status, mod.info.objval,
+                     mod.solution.u_curr, mod.solution.z_curr, mod.solution.l_curr, mod.membuf[24:27]))
+        mod.close()
+    assert outs[0][:5] == outs[1][:5]
+    for a, b in zip(outs[0][5:], outs[1][5:]):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_vector_and_membuf_round_trip(case9_grid):
     env, mod = _env_mod(ea.CASE9)
     rng = np.random.default_rng(0)
