@@ -64,6 +64,8 @@ struct ea_handle {
     double t_x = 0.0, t_bus = 0.0;              // summed durations (kernel_timing only)
     long long n_timed = 0;                      // iterations those sums cover (no-op launches after `done` excluded)
     int kernel_timing = 0;
+    void *flush_buf = nullptr;                  // option "l2_flush_mb": memset before every timed iteration (kernel_timing only)
+    size_t flush_bytes = 0;
     int loopback = 0;                           // tests: exchange done by the caller through the host
     std::vector<cudaEvent_t> kev;               // event pool for kernel_timing
     cudaEvent_t span0 = nullptr, span1 = nullptr;
@@ -432,6 +434,7 @@ void ea_destroy(ea_handle_t *h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void *p : h->peer_maps) if (p) cudaIpcCloseMemHandle(p);
     if (h->xbuf) cudaFree(h->xbuf);
+    if (h->flush_buf) cudaFree(h->flush_buf);
     if (h->gather_host) cudaFreeHost(h->gather_host);
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -627,6 +630,8 @@ static int enqueue_iteration(ea_handle *h, int max_auglag, double mu_max, double
             h->kev.push_back(ev);
         }
         e = &h->kev[3 * slot];
+        // measurement mode: evict the L2 (a write larger than it) before the iteration, outside the event brackets
+        if (h->flush_buf) CK(cudaMemsetAsync(h->flush_buf, slot & 0xff, h->flush_bytes, h->stream));
         CK(cudaEventRecord(e[0], h->stream));
     }
     int rc = launch_x(h, 0, 0, max_auglag, mu_max, scale, 1, 1);
@@ -942,6 +947,19 @@ int ea_set_option(ea_handle_t *h, const char *name, double value) {
     if (!strcmp(name, "chunk")) { h->default_chunk = std::max(1, (int)value); return EA_OK; }
     if (!strcmp(name, "kernel_timing")) { h->kernel_timing = value != 0.0; return EA_OK; }
     if (!strcmp(name, "use_graph")) { h->use_graph = value != 0.0; return EA_OK; }
+    if (!strcmp(name, "l2_flush_mb")) {             // > 0: with kernel_timing, write this many MB before every iteration
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->flush_buf) { cudaFree(h->flush_buf); h->flush_buf = nullptr; h->flush_bytes = 0; }
+        if (value > 0.0) {
+            h->flush_bytes = (size_t)(value * 1048576.0);
+            if (cudaMalloc(&h->flush_buf, h->flush_bytes) != cudaSuccess) {
+                h->flush_buf = nullptr; h->flush_bytes = 0;
+                return fail(h, EA_ERR_ALLOC, "ea_set_option: cannot allocate the L2 flush buffer");
+            }
+        }
+        return EA_OK;
+    }
     return fail(h, EA_ERR_ARG, "ea_set_option: unknown option '%s'", name);
 }
 
