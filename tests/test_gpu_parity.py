@@ -159,6 +159,33 @@ def test_per_iterate_parity_case1354_like():
     _lockstep(d, 4e2, 4e4, 25, True, tol=1e-7)
 
 
+def test_per_iterate_parity_case13659_like():
+    """BASELINE config 3 size (13659 buses / 4092 generators / 20467 branches), rho as in the config, 12 iterations in
+    lock-step with the oracle (8 host threads): u, xbar, z, lambda, the penalty ladder and the four norms."""
+    from exaadmm_b200.synthetic import named_case
+    import os
+    d = named_case("case13659pegase")
+    env = AdmmEnv(d, 5e1, 5e3, use_gpu=True, verbose=0, tight_factor=0.99)
+    mod = ModelAcopf(env)
+    opar = Parameters(); opar.verbose = 0
+    om = OracleModel(mod.grid_data, opar, 5e1, 5e3)
+    om.set_threads(min(8, os.cpu_count() or 1))
+    ops.admm_increment_outer(env, mod); ops.admm_outer_prestep(env, mod); ops.admm_increment_reset_inner(env, mod)
+    om.admm_increment_outer(); om.admm_outer_prestep(); om.admm_increment_reset_inner()
+    worst = 0.0
+    for _ in range(12):
+        ores = om.inner_iteration()
+        ops.admm_increment_inner(env, mod); ops.admm_inner_iteration(env, mod)
+        for name in ("u_curr", "v_curr", "z_curr"):
+            worst = max(worst, float(np.abs(getattr(mod.solution, name) - om.vec(name)).max()))
+        worst = max(worst, float(np.abs(mod.solution.l_curr - om.vec("l_curr")).max()) / env.params.beta)
+        got = np.array([mod.info.primres, mod.info.dualres, mod.info.norm_z_curr, mod.info.mismatch])
+        np.testing.assert_allclose(got, ores, rtol=1e-6, atol=1e-9)
+    np.testing.assert_array_equal(mod.membuf[26], om.membuf()[26])
+    mod.close()
+    assert worst <= 1e-6, worst          # rejected-step decisions within rounding of their threshold, as at 1354 buses
+
+
 def test_per_iterate_parity_case1354_like_readme_rho():
     """BASELINE config 2 (rho_pq=1e1, rho_va=1e3). On the synthetic stand-in this rho puts many
     branch problems in a non-convex regime (rejected TRON steps); a
