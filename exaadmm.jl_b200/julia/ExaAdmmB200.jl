@@ -86,19 +86,38 @@ handle(mod::Mod) = mod.solution.u_curr.handle
 The H2D part of the `ModelAcopf` constructor (acopf_model.jl:41-94): pass the host `GridData`
 (built with the reference's own loader, use_gpu=false) to `ea_create`.
 """
+# `ea_grid_t` over the host arrays of `g` (valid while `g` is alive: callers wrap the ccall in GC.@preserve g)
+grid_struct(g) = EaGrid(g.ngen, g.nline, g.nbus, g.baseMVA,
+    pointer(g.pgmin), pointer(g.pgmax), pointer(g.qgmin), pointer(g.qgmax), pointer(g.c2), pointer(g.c1), pointer(g.c0),
+    pointer(g.YshR), pointer(g.YshI), pointer(g.YffR), pointer(g.YffI), pointer(g.YftR), pointer(g.YftI),
+    pointer(g.YttR), pointer(g.YttI), pointer(g.YtfR), pointer(g.YtfI),
+    pointer(g.FrVmBound), pointer(g.ToVmBound), pointer(g.FrVaBound), pointer(g.ToVaBound), pointer(g.rateA),
+    pointer(g.FrStart), pointer(g.ToStart), pointer(g.GenStart), pointer(g.FrIdx), pointer(g.ToIdx), pointer(g.GenIdx),
+    pointer(g.Pd), pointer(g.Qd), pointer(g.Vmin), pointer(g.Vmax), pointer(g.brBusIdx))
+
 function create_handle(g, gpu_no::Int)
     GC.@preserve g begin
-        grid = EaGrid(g.ngen, g.nline, g.nbus, g.baseMVA,
-            pointer(g.pgmin), pointer(g.pgmax), pointer(g.qgmin), pointer(g.qgmax), pointer(g.c2), pointer(g.c1), pointer(g.c0),
-            pointer(g.YshR), pointer(g.YshI), pointer(g.YffR), pointer(g.YffI), pointer(g.YftR), pointer(g.YftI),
-            pointer(g.YttR), pointer(g.YttI), pointer(g.YtfR), pointer(g.YtfI),
-            pointer(g.FrVmBound), pointer(g.ToVmBound), pointer(g.FrVaBound), pointer(g.ToVaBound), pointer(g.rateA),
-            pointer(g.FrStart), pointer(g.ToStart), pointer(g.GenStart), pointer(g.FrIdx), pointer(g.ToIdx), pointer(g.GenIdx),
-            pointer(g.Pd), pointer(g.Qd), pointer(g.Vmin), pointer(g.Vmax), pointer(g.brBusIdx))
         out = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:ea_create, LIB), Cint, (Ref{EaGrid}, Cint, Ref{Ptr{Cvoid}}), grid, gpu_no, out)
+        rc = ccall((:ea_create, LIB), Cint, (Ref{EaGrid}, Cint, Ref{Ptr{Cvoid}}), grid_struct(g), gpu_no, out)
         rc == 0 || error("ea_create ($rc): " * unsafe_string(ccall((:ea_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
         return out[]
+    end
+end
+
+# An owned library handle kept in a model field (`gen_solution` slot of the multi-period and QP models); the finalizer
+# calls the matching destructor (:ea_destroy, :ea_mp_destroy or :ea_qp_destroy).
+mutable struct B200Handle <: AbstractSolution{Float64,TD}
+    handle::Ptr{Cvoid}
+    function B200Handle(h::Ptr{Cvoid}, destructor::Symbol)
+        obj = new(h)
+        finalizer(obj) do o
+            o.handle == C_NULL && return
+            destructor === :ea_qp_destroy ? ccall((:ea_qp_destroy, LIB), Cvoid, (Ptr{Cvoid},), o.handle) :
+            destructor === :ea_mp_destroy ? ccall((:ea_mp_destroy, LIB), Cvoid, (Ptr{Cvoid},), o.handle) :
+                                            ccall((:ea_destroy, LIB), Cvoid, (Ptr{Cvoid},), o.handle)
+            o.handle = C_NULL
+        end
+        return obj
     end
 end
 
@@ -227,8 +246,9 @@ function init_solution!(mod::QpMod, sol, rho_pq::Float64, rho_va::Float64, devic
     GC.@preserve keep begin
         data = EaQpsubData(map(pointer, keep)...)
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        qp_check(C_NULL, ccall((:ea_qp_create, LIB), Cint, (Ref{EaGrid}, Ref{EaQpsubData}, Cint, Ref{Ptr{Cvoid}}),
-                               grid_struct(mod.grid_data), data, 0, h))
+        g = mod.grid_data
+        GC.@preserve g qp_check(C_NULL, ccall((:ea_qp_create, LIB), Cint, (Ref{EaGrid}, Ref{EaQpsubData}, Cint, Ref{Ptr{Cvoid}}),
+                                              grid_struct(g), data, 0, h))
     end
     mod.gen_solution = B200Handle(h[], :ea_qp_destroy)   # finalizer -> ea_qp_destroy
     qp_check(h[], ccall((:ea_qp_init_solution, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble), h[], rho_pq, rho_va)); return
