@@ -55,7 +55,9 @@ template <int STRIDE> struct TileView {
     EA_DEV double xt(int k) const { return base[(16 + k) * STRIDE]; }
     EA_DEV double Y(int k) const { return base[(24 + k) * STRIDE]; }
 };
-constexpr int TILE_ROWS = 32 + 9;                        // lam, rho, xt, Y + xl0..3, xu0..3, rateA
+constexpr int COLD_ROWS = 10;                            // Lane::xc (6) + Lane::Fc (4)
+constexpr int TILE_ROWS = 32 + 9 + COLD_ROWS;            // lam, rho, xt, Y + xl0..3, xu0..3, rateA + the lane's cold state
+constexpr int TILE_COLD = 32 + 9;                        // first cold row
 
 struct PowTable {      // host-computed (glibc) 1/mu^0.1 and mu^0.9 for the mu sequence 10, 100, ... <= mu_max
     int n;
@@ -194,11 +196,18 @@ enum Phase : int { NEED = 0, START = 1, RESTORE = 2, TRIAL = 3, DONE = 4 };
 
 // State of one branch solve (registers).
 struct Lane {
-    double x[N], xc[N], g[N];
+    double x[N], g[N];
     Sym6 A;
     double ls[2], mu;                       // AL state (membuf rows 25-27)
     double f, fc, delta, alphac, prered, g0, snorm, eta, inv_p01, p09;
-    double Fc[4];                           // flows at the current accepted point
+    // State that is written once per TRON step and read once per solve (or only when a step is rejected) stays out of
+    // the register file - the lone lane's round is bound by it: xc (the point the step started from, N values) and Fc
+    // (flows at the current accepted point, 4 values) live at cold[k * cs]: a shared-memory column in the kernels, a
+    // plain array in the host harness.
+    double *cold;
+    int cs;
+    EA_DEV double &xc(int i) const { return cold[i * cs]; }
+    EA_DEV double &Fc(int k) const { return cold[(N + k) * cs]; }
     int nfev, minor, iter, it_al;
     int phase;
     bool step_pending;
@@ -218,9 +227,9 @@ EA_DEV void begin(Lane &L, const PowTable &T) {
     L.step_pending = false;
     L.evals = L.cg = L.shifts = L.rejected = L.hit_max = 0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) { L.g[i] = 0.0; L.xc[i] = L.x[i]; }
+    for (int i = 0; i < N; ++i) { L.g[i] = 0.0; L.xc(i) = L.x[i]; }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) L.Fc[k] = 0.0;
+    for (int k = 0; k < 4; ++k) L.Fc(k) = 0.0;
 }
 
 // One evaluation phase. pass 0 serves lanes holding a trial point, pass 1 lanes at
@@ -241,7 +250,7 @@ EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N]
     if (pass == 1) {
         L.f = fn;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) L.Fc[k] = Fn[k];
+        for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
         if (L.phase == START) {                      // task 0: a fresh TRON solve
             L.nfev = 1; L.minor = 1; L.iter = 1; L.alphac = 1.0;
             L.delta = tron::nrm2<N>(L.g);            // tron_kernel.jl:102-105
@@ -255,7 +264,7 @@ EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N]
     if (L.nfev >= max_feval) {
         tron_done = true;                            // driver stops, trial point kept (tron_kernel.jl:72-75)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) L.Fc[k] = Fn[k];
+        for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
     } else {
         bool accepted;
         const int task = tron::judge_step(fn, L.fc, L.g0, L.snorm, L.prered, L.iter == 1, L.delta, accepted);
@@ -263,7 +272,7 @@ EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N]
             L.iter++;
             L.f = fn;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) L.Fc[k] = Fn[k];
+            for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
             if (task == 2) tron_done = true;
             else {
                 L.minor++;                            // the reference evaluates g,H here (task GH)
@@ -274,7 +283,7 @@ EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N]
         } else {
             L.rejected++;
 #pragma unroll
-            for (int i = 0; i < N; ++i) L.x[i] = L.xc[i];
+            for (int i = 0; i < N; ++i) L.x[i] = L.xc(i);
             L.f = L.fc;
             if (task == 2) tron_done = true;          // Fc still holds the flows at xc
             else L.phase = RESTORE;                   // g, A must be re-evaluated at xc before the next step
@@ -284,8 +293,8 @@ EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N]
 
     // augmented-Lagrangian update on the line limits (auglag_gpu.jl:96-131)
     L.it_al++;
-    const double cviol1 = L.Fc[0] * L.Fc[0] + L.Fc[1] * L.Fc[1] + L.x[4];
-    const double cviol2 = L.Fc[2] * L.Fc[2] + L.Fc[3] * L.Fc[3] + L.x[5];
+    const double cviol1 = L.Fc(0) * L.Fc(0) + L.Fc(1) * L.Fc(1) + L.x[4];
+    const double cviol2 = L.Fc(2) * L.Fc(2) + L.Fc(3) * L.Fc(3) + L.x[5];
     const double cnorm = tron::dmax(fabs(cviol1), fabs(cviol2));
     bool terminate = false;
     if (cnorm <= L.eta) {
@@ -311,7 +320,7 @@ EA_DEV void compute(Lane &L, const double (&xl)[N], const double (&xu)[N]) {
     if (!L.step_pending) return;
     L.fc = L.f;
 #pragma unroll
-    for (int i = 0; i < N; ++i) L.xc[i] = L.x[i];
+    for (int i = 0; i < N; ++i) L.xc(i) = L.x[i];
     tron::Stats st;
     tron::compute_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered, L.g0, L.snorm, st);
     L.cg += st.cg;

@@ -277,8 +277,8 @@ __device__ __forceinline__ void load_bounds(const double *col, double (&xl)[6], 
 __device__ __forceinline__ void store_branch(const Dev &d, int I, const branch::Lane &L) {
     const int nl = d.nline;
     d4 of, ot;
-    of.p = L.Fc[0]; of.q = L.Fc[1]; of.w = L.x[0] * L.x[0]; of.t = L.x[2];
-    ot.p = L.Fc[2]; ot.q = L.Fc[3]; ot.w = L.x[1] * L.x[1]; ot.t = L.x[3];
+    of.p = L.Fc(0); of.q = L.Fc(1); of.w = L.x[0] * L.x[0]; of.t = L.x[2];
+    ot.p = L.Fc(2); ot.q = L.Fc(3); ot.w = L.x[1] * L.x[1]; ot.t = L.x[3];
     st4(d.u + d.gpad, d.slot_from[I], of);
     st4(d.u + d.gpad, d.slot_to[I], ot);
     d.als[I] = L.ls[0]; d.als[nl + I] = L.ls[1]; d.als[2 * nl + I] = L.mu;
@@ -310,6 +310,7 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
     double *col = tile + threadIdx.x;
     const branch::Objective<branch::TileView<XBLOCK>> eval{ { col }, scale };
     branch::Lane L;
+    L.cold = tile + branch::TILE_COLD * XBLOCK + threadIdx.x; L.cs = XBLOCK;
     // Small grids: fewer lanes per warp, more warps. A round of the state machine costs a warp ~14 us when its 32 lanes
     // sit in different phases of different branches, ~7.5 us when only a few lanes are live; with fewer branches than
     // resident lanes the work is spread over all warps instead of filling the first ones.

@@ -106,6 +106,7 @@ k_xupdate_mp(MpDev m, int nline, branch::PowTable T, long long major_arg, int zs
     double *col = tile + threadIdx.x;
     const branch::Objective<branch::TileView<XBLOCK>> eval{ { col }, scale };
     branch::Lane L;
+    L.cold = tile + branch::TILE_COLD * XBLOCK + threadIdx.x; L.cs = XBLOCK;
     // (no spreading of small grids over all warps here, unlike k_xupdate: the generator kernel runs beside this one
     //  on the side stream and needs the SMs this launch leaves free - measured: -5 % at 1354 buses x 6 periods)
     L.phase = branch::NEED;

@@ -47,13 +47,15 @@ static void run(const Eval &eval, double *x, const double *xl, const double *xu,
     branch::PowTable T;
     make_pow_table(T, mu_max);
     branch::Lane L;
+    double cold[branch::COLD_ROWS];
+    L.cold = cold; L.cs = 1;
     double l[6], u[6];
     for (int k = 0; k < 6; ++k) { L.x[k] = x[k]; l[k] = xl[k]; u[k] = xu[k]; }
     L.ls[0] = param[24]; L.ls[1] = param[25];
     L.mu = (major_iter == 1) ? 10.0 : param[26];
     branch::solve(L, eval, l, u, max_auglag, mu_max, T);
     for (int k = 0; k < 6; ++k) x[k] = L.x[k];
-    if (F) for (int k = 0; k < 4; ++k) F[k] = L.Fc[k];
+    if (F) for (int k = 0; k < 4; ++k) F[k] = L.Fc(k);
     param[24] = L.ls[0]; param[25] = L.ls[1]; param[26] = L.mu;
     work[0] = L.it_al; work[1] = L.evals; work[2] = L.cg; work[3] = L.shifts; work[4] = L.rejected; work[5] = L.hit_max;
 }
