@@ -55,7 +55,7 @@ template <int STRIDE> struct TileView {
     EA_DEV double xt(int k) const { return base[(16 + k) * STRIDE]; }
     EA_DEV double Y(int k) const { return base[(24 + k) * STRIDE]; }
 };
-constexpr int COLD_ROWS = 10;                            // Lane::xc (6) + Lane::Fc (4)
+constexpr int COLD_ROWS = 18;                            // Lane::xc (6), Fc (4), eta, inv_p01, p09, f, fc, prered, g0, snorm
 constexpr int TILE_ROWS = 32 + 9 + COLD_ROWS;            // lam, rho, xt, Y + xl0..3, xu0..3, rateA + the lane's cold state
 constexpr int TILE_COLD = 32 + 9;                        // first cold row
 
@@ -199,15 +199,24 @@ struct Lane {
     double x[N], g[N];
     Sym6 A;
     double ls[2], mu;                       // AL state (membuf rows 25-27)
-    double f, fc, delta, alphac, prered, g0, snorm, eta, inv_p01, p09;
-    // State that is written once per TRON step and read once per solve (or only when a step is rejected) stays out of
-    // the register file - the lone lane's round is bound by it: xc (the point the step started from, N values) and Fc
-    // (flows at the current accepted point, 4 values) live at cold[k * cs]: a shared-memory column in the kernels, a
-    // plain array in the host harness.
+    double delta, alphac;
+    // State that is written once per TRON step and read once per step or per solve stays out of the register file - the
+    // lone lane's round is bound by it. It lives at cold[k * cs] (a shared-memory column in the kernels, a plain array
+    // in the host harness): xc (the point the step started from), Fc (flows at the current accepted point), the AL
+    // thresholds eta / 1/mu^0.1 / mu^0.9, and the scalars that travel from the step to its evaluation (f, fc, prered,
+    // g's, |s|).
     double *cold;
     int cs;
     EA_DEV double &xc(int i) const { return cold[i * cs]; }
     EA_DEV double &Fc(int k) const { return cold[(N + k) * cs]; }
+    EA_DEV double &eta() const { return cold[(N + 4) * cs]; }
+    EA_DEV double &inv_p01() const { return cold[(N + 5) * cs]; }
+    EA_DEV double &p09() const { return cold[(N + 6) * cs]; }
+    EA_DEV double &f() const { return cold[(N + 7) * cs]; }
+    EA_DEV double &fc() const { return cold[(N + 8) * cs]; }
+    EA_DEV double &prered() const { return cold[(N + 9) * cs]; }
+    EA_DEV double &g0() const { return cold[(N + 10) * cs]; }
+    EA_DEV double &snorm() const { return cold[(N + 11) * cs]; }
     int nfev, minor, iter, it_al;
     int phase;
     bool step_pending;
@@ -218,9 +227,9 @@ struct Lane {
 // Start a branch: x, ls, mu must be set by the caller (mu = 10 on the first inner
 // iteration of an outer iteration, acopf_auglag_linelimit_kernel_gpu.jl:75-80).
 EA_DEV void begin(Lane &L, const PowTable &T) {
-    mu_powers(T, L.mu, L.inv_p01, L.p09);
-    L.eta = L.inv_p01;                       // eta = 1/mu^0.1 (:84)
-    L.f = L.fc = L.delta = L.prered = L.g0 = L.snorm = 0.0;
+    mu_powers(T, L.mu, L.inv_p01(), L.p09());
+    L.eta() = L.inv_p01();                       // eta = 1/mu^0.1 (:84)
+    L.f() = L.fc() = L.delta = L.prered() = L.g0() = L.snorm() = 0.0;
     L.alphac = 1.0;
     L.nfev = 0; L.minor = 0; L.iter = 1; L.it_al = 0;
     L.phase = START;
@@ -248,7 +257,7 @@ EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N]
     if (L.phase != RESTORE) L.evals++;               // counted like the reference's f-evaluations
 
     if (pass == 1) {
-        L.f = fn;
+        L.f() = fn;
 #pragma unroll
         for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
         if (L.phase == START) {                      // task 0: a fresh TRON solve
@@ -267,10 +276,10 @@ EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N]
         for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
     } else {
         bool accepted;
-        const int task = tron::judge_step(fn, L.fc, L.g0, L.snorm, L.prered, L.iter == 1, L.delta, accepted);
+        const int task = tron::judge_step(fn, L.fc(), L.g0(), L.snorm(), L.prered(), L.iter == 1, L.delta, accepted);
         if (accepted) {
             L.iter++;
-            L.f = fn;
+            L.f() = fn;
 #pragma unroll
             for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
             if (task == 2) tron_done = true;
@@ -284,7 +293,7 @@ EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N]
             L.rejected++;
 #pragma unroll
             for (int i = 0; i < N; ++i) L.x[i] = L.xc(i);
-            L.f = L.fc;
+            L.f() = L.fc();
             if (task == 2) tron_done = true;          // Fc still holds the flows at xc
             else L.phase = RESTORE;                   // g, A must be re-evaluated at xc before the next step
         }
@@ -297,17 +306,17 @@ EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N]
     const double cviol2 = L.Fc(2) * L.Fc(2) + L.Fc(3) * L.Fc(3) + L.x[5];
     const double cnorm = tron::dmax(fabs(cviol1), fabs(cviol2));
     bool terminate = false;
-    if (cnorm <= L.eta) {
+    if (cnorm <= L.eta()) {
         if (cnorm <= 1e-6) terminate = true;
         else {
             L.ls[0] += L.mu * cviol1;
             L.ls[1] += L.mu * cviol2;
-            L.eta = L.eta / L.p09;
+            L.eta() = L.eta() / L.p09();
         }
     } else {
         L.mu = tron::dmin(mu_max, L.mu * 10.0);
-        mu_powers(T, L.mu, L.inv_p01, L.p09);
-        L.eta = L.inv_p01;
+        mu_powers(T, L.mu, L.inv_p01(), L.p09());
+        L.eta() = L.inv_p01();
     }
     if (L.it_al >= max_auglag) { if (!terminate) L.hit_max = 1; terminate = true; }
     if (terminate) { L.phase = DONE; return true; }
@@ -318,11 +327,11 @@ EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N]
 // dtron COMPUTE for lanes with a pending step: Cauchy point + projected CG -> trial point in x.
 EA_DEV void compute(Lane &L, const double (&xl)[N], const double (&xu)[N]) {
     if (!L.step_pending) return;
-    L.fc = L.f;
+    L.fc() = L.f();
 #pragma unroll
     for (int i = 0; i < N; ++i) L.xc(i) = L.x[i];
     tron::Stats st;
-    tron::compute_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered, L.g0, L.snorm, st);
+    tron::compute_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st);
     L.cg += st.cg;
     L.shifts += st.shifts;
     L.phase = TRIAL;
