@@ -318,7 +318,7 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
     L.phase = (lane < lanes_on) ? branch::NEED : branch::DONE;
     L.step_pending = false;
     int I = -1;
-    unsigned long long work[7] = { 0, 0, 0, 0, 0, 0, 0 };  // calls, auglag, evals, cg, shifts, rejected, hit_max
+    unsigned work[7] = { 0, 0, 0, 0, 0, 0, 0 };            // calls, auglag, evals, cg, shifts, rejected, hit_max (per lane: 32 bits)
     int mx = 0;
 
 #pragma unroll 1
@@ -378,7 +378,7 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
         }
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 7; ++k) if (work[k]) atomicAdd(&d.counters->v[k], work[k]);
+            for (int k = 0; k < 7; ++k) if (work[k]) atomicAdd(&d.counters->v[k], (unsigned long long)work[k]);
             atomicMax(&d.counters->v[7], (unsigned long long)mx);
         }
     }
