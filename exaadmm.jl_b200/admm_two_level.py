@@ -62,7 +62,7 @@ def _native(env, mod):
     par.beta = out.beta
 
 
-def admm_two_level(env, mod, device=None, mode: str = "fused"):
+def admm_two_level(env, mod, device=None, mode: str = "fused", talk: bool = True):
     par, info = env.params, mod.info
     if mode == "native":
         if getattr(mod, "is_multiperiod", False):
@@ -70,7 +70,7 @@ def admm_two_level(env, mod, device=None, mode: str = "fused"):
             admm_two_level_native(env, mod)
         else:
             _native(env, mod)
-        if par.verbose > 0:
+        if par.verbose > 0 and talk:          # talk: rank 0 of a partitioned solve (every rank passes the same verbose)
             print_statistics(env, mod)
         return
 

@@ -299,9 +299,13 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
         const int64_t fs = G->FrStart[b] - 1, ts = G->ToStart[b] - 1, gs = G->GenStart[b] - 1;
         if (fs < 0 || fs > nline || ts < 0 || ts > nline || gs < 0 || gs > ngen)
             return bail(fail(h, EA_ERR_ARG, "ea_create: CSR pointer out of range at bus %d", b));
+        if (b > 0 && (G->FrStart[b] < G->FrStart[b - 1] || G->ToStart[b] < G->ToStart[b - 1] || G->GenStart[b] < G->GenStart[b - 1]))
+            return bail(fail(h, EA_ERR_ARG, "ea_create: CSR pointers are not monotonic at bus %d", b));
         hstart[b] = (int)(fs + ts);
         gstart[b] = (int)gs;
     }
+    if (G->FrStart[0] != 1 || G->ToStart[0] != 1 || G->GenStart[0] != 1)
+        return bail(fail(h, EA_ERR_ARG, "ea_create: CSR pointers must start at 1"));
     if (hstart[nbus] != 2 * nline || gstart[nbus] != ngen)
         return bail(fail(h, EA_ERR_ARG, "ea_create: CSR pointers do not cover all lines/generators"));
     for (int b = 0; b < nbus; ++b) {
@@ -323,6 +327,10 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
             h->gen_of_slot[k] = (int)g;
         }
     }
+    for (int l = 0; l < nline; ++l)
+        if (slot_from[l] < 0 || slot_to[l] < 0) return bail(fail(h, EA_ERR_ARG, "ea_create: line %d is missing from FrIdx / ToIdx", l));
+    for (int g = 0; g < ngen; ++g)
+        if (slot_of_gen[g] < 0) return bail(fail(h, EA_ERR_ARG, "ea_create: generator %d is missing from GenIdx", g));
     std::vector<int> ref2int((size_t)h->nvar);
     for (int g = 0; g < ngen; ++g) { ref2int[2 * g] = 2 * slot_of_gen[g]; ref2int[2 * g + 1] = 2 * slot_of_gen[g] + 1; }
     for (int l = 0; l < nline; ++l) {

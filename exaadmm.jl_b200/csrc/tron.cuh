@@ -57,6 +57,12 @@ EA_DEV double dmax(double a, double b) { return a > b ? a : b; }
 // construction); EA_EXACT and the host use the correctly rounded operations.
 EA_DEV double ddiv(double a, double b) {
 #if defined(__CUDA_ARCH__) && !EA_EXACT
+    // the refinement needs a normal divisor well inside the exponent range (rcp.approx flushes subnormals to zero and
+    // 1/b must not overflow): anything else - a subnormal gradient component in breakpt, a bus without branch ends -
+    // takes the IEEE division, so that the result is what the reference computes (possibly inf / NaN) and not a NaN
+    // made by the Newton steps
+    const unsigned ex = ((unsigned)__double2hiint(b) >> 20) & 0x7ffu;
+    if (__builtin_expect(ex - 64u >= 1920u, 0)) return a / b;
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     r = fma(fma(-b, r, 1.0), r, r);

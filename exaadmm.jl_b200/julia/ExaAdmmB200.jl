@@ -11,10 +11,14 @@
 module ExaAdmmB200
 
 using ExaAdmm
-import ExaAdmm: AdmmEnv, AbstractOPFModel, ModelAcopf, GridData, Solution, IterationInformation,
-                ComponentInformation, admm_increment_outer, admm_increment_reset_inner, admm_increment_inner,
-                admm_outer_prestep, admm_inner_prestep, admm_update_x, admm_update_xbar, admm_update_z,
-                admm_update_l, admm_update_residual, admm_update_lz, admm_poststep, admm_two_level, init_solution!
+# ExaAdmm exports only its solve_* entry points (src/ExaAdmm.jl), so every type and generic function that gets a method
+# here is imported by name: a method defined on an un-imported name would create a new local function instead of
+# extending ExaAdmm's.
+import ExaAdmm: AdmmEnv, AbstractOPFModel, AbstractSolution, ModelAcopf, ModelMpacopf, ModelQpsub, GridData, Solution,
+                IterationInformation, ComponentInformation, admm_increment_outer, admm_increment_reset_inner,
+                admm_increment_inner, admm_outer_prestep, admm_inner_prestep, admm_update_x, admm_update_xbar,
+                admm_update_z, admm_update_l, admm_update_l_single, admm_update_residual, admm_update_lz, admm_poststep,
+                admm_two_level, admm_one_level, init_solution!, print_statistics
 
 const LIB = get(ENV, "EXAADMM_B200_LIB", "libexaadmm_b200.so")
 
@@ -175,7 +179,7 @@ function admm_two_level(env::Env, mod::Mod, device=nothing)
     i.time_l_update, i.time_lz_update, i.time_overall = info.time_l_update, info.time_lz_update, info.time_overall
     i.user.time_generators, i.user.time_branches, i.user.time_buses = info.time_generators, info.time_branches, info.time_buses
     p.beta = info.beta
-    p.verbose > 0 && ExaAdmm.print_statistics(env, mod)
+    p.verbose > 0 && print_statistics(env, mod)
     return
 end
 
@@ -187,6 +191,23 @@ const MpMod = ModelMpacopf{Float64,TD,TI,TM}
 mp_handle(mod::MpMod) = mod.models[1].gen_solution.handle      # the ea_mp_handle_t* is kept in the gen_solution slot
 mp_check(h, rc) = rc == 0 || error(unsafe_string(ccall((:ea_mp_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
 
+# Without these four the calls would fall through to the single-period methods above, whose handle(mod) reads
+# mod.solution.u_curr - a Vector of ramp solutions for this model.
+function init_solution!(mod::MpMod, sol, rho_pq::Float64, rho_va::Float64, device=nothing)
+    mp_check(mp_handle(mod), ccall((:ea_mp_init_solution, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble), mp_handle(mod), rho_pq, rho_va)); return
+end
+function admm_outer_prestep(env::Env, mod::MpMod, device=nothing)
+    out = Ref{Cdouble}(0)
+    mp_check(mp_handle(mod), ccall((:ea_mp_outer_prestep, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), mp_handle(mod), out))
+    mod.info.norm_z_prev = out[]; return
+end
+admm_inner_prestep(env::Env, mod::MpMod, device=nothing) =
+    (mp_check(mp_handle(mod), ccall((:ea_mp_inner_prestep, LIB), Cint, (Ptr{Cvoid},), mp_handle(mod))); nothing)
+function admm_poststep(env::Env, mod::MpMod, device=nothing)
+    obj = Ref{Cdouble}(0); err = Ref{Cdouble}(0)
+    mp_check(mp_handle(mod), ccall((:ea_mp_poststep, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Cdouble}), mp_handle(mod), obj, err))
+    mod.info.objval = obj[]; mod.info.user.err_ramp = err[]; return
+end
 function admm_update_x(env::Env, mod::MpMod, device=nothing)
     p = env.params
     mp_check(mp_handle(mod), ccall((:ea_mp_update_x, LIB), Cint, (Ptr{Cvoid}, Int64, Int32, Cdouble, Cdouble),

@@ -96,8 +96,11 @@ def solve_acopf_partitioned(case, rank: int, world: int, *, outer_iterlim=20, in
         init_peer_exchange(mod)
     p = env.params
     p.scale, p.obj_scale, p.outer_eps, p.outer_iterlim, p.inner_iterlim = scale, obj_scale, outer_eps, outer_iterlim, inner_iterlim
-    p.verbose = verbose if rank == 0 else 0
-    admm_two_level(env, mod, None, mode="native")
+    # the SAME verbose on every rank: ea_admm_two_level picks its control path (one exchange per host round trip vs
+    # chunks of iterations) from it, and ranks on different paths would issue different numbers of collectives. The
+    # library prints on rank 0 only; the statistics block printed from here likewise.
+    p.verbose = verbose
+    admm_two_level(env, mod, None, mode="native", talk=(rank == 0))
     return env, mod, lg
 
 

@@ -189,6 +189,25 @@ def test_warm_start_solve_matches_oracle(tmp_path, case9_grid):
     mod.close()
 
 
+def test_period_solo_solves_are_plain_single_period_solves(tmp_path):
+    """The warm start of solve_mpacopf (solve_mpacopf.jl:27-32) solves every period ALONE as a ModelAcopf: the period
+    handles of a multi-period model must not see the ramp coupling. Grid with binding line limits, so the multipliers
+    the solo solves leave in membuf (rows 25-27) matter for the coupled solve that follows."""
+    case = synthetic_case(120, 25, 170, seed=120, rate_margin=1.02)
+    grid = ea.GridData.from_opfdata(case)
+    scales = [1.0, 1.02, 0.98]
+    env, mod, om = make_models(tmp_path, case, grid, scales, outer_iterlim=3, inner_iterlim=60)
+    for t, (m, o) in enumerate(zip(mod.models, om.models)):
+        admm_two_level(env, m, None, mode="native")
+        oi = o.admm_two_level()
+        assert m.info.cumul > 0 and (m.info.outer, m.info.cumul) == (oi.outer, oi.cumul), (t, vars(m.info))
+        assert m.info.objval == pytest.approx(oi.objval, rel=1e-8)
+        np.testing.assert_allclose(m.solution.u_curr, o.vec("u_curr"), atol=1e-6, err_msg=f"period {t} u")
+        np.testing.assert_allclose(m.membuf[24:27], o.membuf()[24:27], rtol=1e-5, atol=1e-6, err_msg=f"period {t} membuf")
+        assert np.abs(o.membuf()[24:26]).max() > 0 or t > 0        # some line limit is active
+    mod.close()
+
+
 def test_single_period_horizon_equals_acopf(tmp_path, case9_grid):
     prefix = write_profile(tmp_path, case9_grid, [1.0])
     env, mod = solve_mpacopf(ea.CASE9, prefix, use_gpu=True, verbose=0, end_period=1, warm_start=False, outer_iterlim=25,
