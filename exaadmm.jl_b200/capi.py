@@ -235,7 +235,7 @@ SIGNATURES = {
     "ea_qp_get_kernel_times": (C.c_int, [_H, _pd]),
     "ea_diag_fp64_peak": (C.c_int, [C.c_int, _pd]),
     "ea_diag_branch_eval": (C.c_int, [C.c_int, C.c_int64, _pd, _pd, _pd, C.c_double, _pd, _pd, _pd]),
-    "ea_diag_branch_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, _pd, C.c_int32, C.c_double, C.c_double, _pd,
+    "ea_diag_branch_solve": (C.c_int, [C.c_int, C.c_int, C.c_int64, _pd, C.c_int32, C.c_double, C.c_double, _pd,
                                        C.POINTER(C.c_int32), C.POINTER(C.c_int64), _pd]),
 }
 

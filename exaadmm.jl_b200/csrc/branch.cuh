@@ -77,31 +77,11 @@ EA_DEV void mu_powers(const PowTable &T, double mu, double &inv_p01, double &p09
     inv_p01 = a; p09 = b;
 }
 
-// ---- f, grad f, Hessian of the scaled branch AL objective -----------------------------------------
-// (acopf_eval_linelimit_kernel_gpu.jl:1-594). The evaluation is split in two:
-//   eval_base(x)            everything that depends on the point only: the four flows, the line-limit
-//                           constraint values c_j, and the objective / gradient / Hessian in the reduced
-//                           variables y = (vi, vj, t = ti - tj) as  base + m_0 * side_0 + m_1 * side_1 + mu * d d'
-//   combine(base, ls, mu)   plugs in the multiplier estimates m_j = ls_j + mu c_j and expands to the 6 x 6 matrix
-// An augmented-Lagrangian update changes (ls, mu) but not x: the next TRON solve starts at the point the last one
-// ended at, so its START evaluation is just `combine` on the base that is still at hand (chain.cuh) - and because a
-// fresh evaluation runs exactly the same two functions, both give the same bits. All arithmetic is written with
-// explicit fused multiply-adds (the library is compiled with -fmad=false: no contraction the source does not spell
-// out), so every instantiation of this code, on the device and in the host harness, rounds identically.
-struct Base {
-    double F[4];          // pij, qij, pji, qji
-    double c[2];          // F0^2 + F1^2 + s_ij,  F2^2 + F3^2 + s_ji
-    double fb;            // objective without the (ls, mu) terms, unscaled
-    double gr[3];         // reduced gradient, part independent of m
-    double gt[2];         // lam6 + rho6 (ti - xt6),  lam7 + rho7 (tj - xt7)
-    double d[2][3];       // grad_y (p^2 + q^2) of side j
-    double Hb[6];         // reduced Hessian (00, 01, 02, 11, 12, 22), part independent of m
-    double Hm[2][6];      // coefficient of m_j: hess_y (p^2 + q^2) of side j
-#ifdef EA_PARITY
-    double x[N];          // the parity build evaluates in the oracle's operation order instead (eval_fgh_ref)
-#endif
-};
-
+// ---- f, grad f, Hessian (packed lower) of the scaled branch AL objective, and the four flows -----------------------
+// F = (pij, qij, pji, qji) (acopf_eval_linelimit_kernel_gpu.jl:1-594, :17-22), fused, in the reduced variables
+// y = (vi, vj, t = ti - tj). All arithmetic is written with explicit fused multiply-adds: the library is compiled with
+// -fmad=false (no contraction the source does not spell out), so every instantiation of this code - the kernels, the
+// diagnostics, the host harness of the tests - rounds identically.
 #ifdef EA_PARITY
 // The oracle's formulas in the oracle's operation order, every operation rounded separately (oracle/acopf_oracle.c:
 // orc_eval_f, orc_eval_gh - themselves restatements of acopf_eval_linelimit_kernel_cpu.jl in compact form): with it
@@ -205,53 +185,41 @@ EA_DEV void eval_fgh_ref(const View &D, const double (&ls)[2], double mu, double
 }
 #endif
 
-// One flow F = a vi^2 + b vj^2 + vi vj P(t) with P = ga cos t + de sin t; flows 0, 1 (from side) have b = 0,
-// flows 2, 3 (to side) a = 0. Accumulates the flow's terms into the base.
+// One flow F = ab v2 + vi vj P(t), P = ga cos t + de sin t: v2 = vi^2, ab = a for the from side (flows 0, 1: b = 0),
+// v2 = vj^2, ab = b for the to side (flows 2, 3: a = 0). Adds the flow's terms to the sums of its side / of the branch.
 template <bool FROM>
-EA_DEV void flow_terms(double ab, double ga, double de, double lam, double rho, double xt, double vi, double vj,
-                       double vv, double v2, double s, double c, double &F, double &fb, double (&gr)[3],
-                       double (&d)[3], double (&Hb)[6], double (&Hm)[6]) {
-    const double P = EA_FMA(ga, c, de * s);
-    const double Q = EA_FMA(de, c, -(ga * s));
-    F = EA_FMA(ab, v2, vv * P);                            // v2 = vi^2 (from side) or vj^2 (to side)
+EA_DEV void flow_terms(double ab, double ga, double de, double lam, double rho, double xt, double m2 /* 2 m_j */,
+                       double vi, double vj, double vv, double P, double Q, double F, double &fv, double &ABs,
+                       double &Ps, double &Qs, double (&d)[3], double (&H)[6]) {
     const double ab2 = 2.0 * ab;
     const double G0 = FROM ? EA_FMA(ab2, vi, vj * P) : vj * P;
     const double G1 = FROM ? vi * P : EA_FMA(ab2, vj, vi * P);
     const double G2 = vv * Q;
     const double dev = F - xt;
+    fv = EA_FMA(lam, F, fv);
+    fv = EA_FMA(0.5 * (rho * dev), dev, fv);
     const double r = EA_FMA(rho, dev, lam);
-    fb = EA_FMA(lam, F, fb);
-    fb = EA_FMA(0.5 * (rho * dev), dev, fb);
+    const double w = EA_FMA(m2, F, r);
+    const double kap = rho + m2;
+    ABs = EA_FMA(w, ab, ABs); Ps = EA_FMA(w, P, Ps); Qs = EA_FMA(w, Q, Qs);
     const double tF = 2.0 * F;
-    // second derivatives of F in y: (00) 2a | 0, (01) P, (02) vj Q, (11) 0 | 2b, (12) vi Q, (22) -vv P
-    const double e02 = vj * Q, e12 = vi * Q, e22 = -(vv * P);
-    gr[0] = EA_FMA(r, G0, gr[0]); gr[1] = EA_FMA(r, G1, gr[1]); gr[2] = EA_FMA(r, G2, gr[2]);
-    d[0] = EA_FMA(tF, G0, d[0]);  d[1] = EA_FMA(tF, G1, d[1]);  d[2] = EA_FMA(tF, G2, d[2]);
-    const double r0 = rho * G0, r1 = rho * G1, r2 = rho * G2;
-    const double t0 = 2.0 * G0, t1 = 2.0 * G1, t2 = 2.0 * G2;
-    Hb[0] = EA_FMA(r0, G0, Hb[0]); Hb[1] = EA_FMA(r0, G1, Hb[1]); Hb[2] = EA_FMA(r0, G2, Hb[2]);
-    Hb[3] = EA_FMA(r1, G1, Hb[3]); Hb[4] = EA_FMA(r1, G2, Hb[4]); Hb[5] = EA_FMA(r2, G2, Hb[5]);
-    Hm[0] = EA_FMA(t0, G0, Hm[0]); Hm[1] = EA_FMA(t0, G1, Hm[1]); Hm[2] = EA_FMA(t0, G2, Hm[2]);
-    Hm[3] = EA_FMA(t1, G1, Hm[3]); Hm[4] = EA_FMA(t1, G2, Hm[4]); Hm[5] = EA_FMA(t2, G2, Hm[5]);
-    if (FROM) { Hb[0] = EA_FMA(r, ab2, Hb[0]); Hm[0] = EA_FMA(tF, ab2, Hm[0]); }
-    else      { Hb[3] = EA_FMA(r, ab2, Hb[3]); Hm[3] = EA_FMA(tF, ab2, Hm[3]); }
-    Hb[1] = EA_FMA(r, P, Hb[1]);   Hm[1] = EA_FMA(tF, P, Hm[1]);
-    Hb[2] = EA_FMA(r, e02, Hb[2]); Hm[2] = EA_FMA(tF, e02, Hm[2]);
-    Hb[4] = EA_FMA(r, e12, Hb[4]); Hm[4] = EA_FMA(tF, e12, Hm[4]);
-    Hb[5] = EA_FMA(r, e22, Hb[5]); Hm[5] = EA_FMA(tF, e22, Hm[5]);
+    d[0] = EA_FMA(tF, G0, d[0]); d[1] = EA_FMA(tF, G1, d[1]); d[2] = EA_FMA(tF, G2, d[2]);
+    const double k0 = kap * G0, k1 = kap * G1, k2 = kap * G2;
+    H[0] = EA_FMA(k0, G0, H[0]); H[1] = EA_FMA(k0, G1, H[1]); H[2] = EA_FMA(k0, G2, H[2]);
+    H[3] = EA_FMA(k1, G1, H[3]); H[4] = EA_FMA(k1, G2, H[4]); H[5] = EA_FMA(k2, G2, H[5]);
 }
 
 template <class View>
-EA_DEV void eval_base(const View &D, const double (&x)[N], Base &B) {
+EA_DEV void eval_fgh(const View &D, const double (&ls)[2], double mu, double scale,
+                     const double (&x)[N], double &f, double (&g)[N], Sym6 &A, double (&F)[4]) {
 #ifdef EA_PARITY
-#pragma unroll
-    for (int i = 0; i < N; ++i) B.x[i] = x[i];
+    eval_fgh_ref(D, ls, mu, scale, x, f, g, A);
     {   // flows as the AL loop of the reference computes them (acopf_auglag_linelimit_kernel_gpu.jl:98-104, 135-138)
         const double cc = x[0] * x[1] * cos(x[2] - x[3]), ss = x[0] * x[1] * sin(x[2] - x[3]);
-        B.F[0] = D.Y(0) * (x[0] * x[0]) + D.Y(2) * cc + D.Y(3) * ss;
-        B.F[1] = -D.Y(1) * (x[0] * x[0]) - D.Y(3) * cc + D.Y(2) * ss;
-        B.F[2] = D.Y(4) * (x[1] * x[1]) + D.Y(6) * cc - D.Y(7) * ss;
-        B.F[3] = -D.Y(5) * (x[1] * x[1]) - D.Y(7) * cc - D.Y(6) * ss;
+        F[0] = D.Y(0) * (x[0] * x[0]) + D.Y(2) * cc + D.Y(3) * ss;
+        F[1] = -D.Y(1) * (x[0] * x[0]) - D.Y(3) * cc + D.Y(2) * ss;
+        F[2] = D.Y(4) * (x[1] * x[1]) + D.Y(6) * cc - D.Y(7) * ss;
+        F[3] = -D.Y(5) * (x[1] * x[1]) - D.Y(7) * cc - D.Y(6) * ss;
     }
 #else
     const double vi = x[0], vj = x[1];
@@ -259,62 +227,57 @@ EA_DEV void eval_base(const View &D, const double (&x)[N], Base &B) {
     sincos(x[2] - x[3], &s, &c);
     const double vv = vi * vj, vi2 = vi * vi, vj2 = vj * vj;
     const double Y0 = D.Y(0), Y1 = D.Y(1), Y2 = D.Y(2), Y3 = D.Y(3), Y4 = D.Y(4), Y5 = D.Y(5), Y6 = D.Y(6), Y7 = D.Y(7);
-    double fb = 0.0;
+    // per flow: a | b, gamma, delta;  P = gamma c + delta s, Q = delta c - gamma s, F = ab v2 + vv P
+    const double ab[4] = { Y0, -Y1, Y4, -Y5 };
+    const double ga[4] = { Y2, -Y3, Y6, -Y7 };
+    const double de[4] = { Y3, Y2, -Y7, -Y6 };
+    double P[4], Q[4];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { B.gr[i] = 0.0; B.d[0][i] = 0.0; B.d[1][i] = 0.0; }
+    for (int k = 0; k < 4; ++k) {
+        P[k] = EA_FMA(ga[k], c, de[k] * s);
+        Q[k] = EA_FMA(de[k], c, -(ga[k] * s));
+        F[k] = EA_FMA(ab[k], (k < 2) ? vi2 : vj2, vv * P[k]);
+    }
+    const double c1 = EA_FMA(F[0], F[0], F[1] * F[1]) + x[4];
+    const double c2 = EA_FMA(F[2], F[2], F[3] * F[3]) + x[5];
+    const double m0 = EA_FMA(mu, c1, ls[0]), m1 = EA_FMA(mu, c2, ls[1]);
+    const double hm = 0.5 * mu;
+    double fv = EA_FMA(hm * c2, c2, EA_FMA(hm * c1, c1, EA_FMA(ls[1], c2, ls[0] * c1)));
+    double As = 0.0, Bs = 0.0, Ps = 0.0, Qs = 0.0;        // sum_k w_k (a, b, P, Q)_k
+    double H[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };       // reduced Hessian: 00, 01, 02, 11, 12, 22
+    double d[2][3] = { { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 } };
+    const double m20 = 2.0 * m0, m21 = 2.0 * m1;
+    flow_terms<true>(ab[0], ga[0], de[0], D.lam(0), D.rho(0), D.xt(0), m20, vi, vj, vv, P[0], Q[0], F[0], fv, As, Ps, Qs, d[0], H);
+    flow_terms<true>(ab[1], ga[1], de[1], D.lam(1), D.rho(1), D.xt(1), m20, vi, vj, vv, P[1], Q[1], F[1], fv, As, Ps, Qs, d[0], H);
+    flow_terms<false>(ab[2], ga[2], de[2], D.lam(2), D.rho(2), D.xt(2), m21, vi, vj, vv, P[2], Q[2], F[2], fv, Bs, Ps, Qs, d[1], H);
+    flow_terms<false>(ab[3], ga[3], de[3], D.lam(3), D.rho(3), D.xt(3), m21, vi, vj, vv, P[3], Q[3], F[3], fv, Bs, Ps, Qs, d[1], H);
+    H[0] = EA_FMA(2.0, As, H[0]); H[3] = EA_FMA(2.0, Bs, H[3]); H[1] += Ps;
+    H[2] = EA_FMA(vj, Qs, H[2]);  H[4] = EA_FMA(vi, Qs, H[4]);  H[5] = EA_FMA(-vv, Ps, H[5]);
 #pragma unroll
-    for (int e = 0; e < 6; ++e) { B.Hb[e] = 0.0; B.Hm[0][e] = 0.0; B.Hm[1][e] = 0.0; }
-    flow_terms<true>(Y0, Y2, Y3, D.lam(0), D.rho(0), D.xt(0), vi, vj, vv, vi2, s, c, B.F[0], fb, B.gr, B.d[0], B.Hb, B.Hm[0]);
-    flow_terms<true>(-Y1, -Y3, Y2, D.lam(1), D.rho(1), D.xt(1), vi, vj, vv, vi2, s, c, B.F[1], fb, B.gr, B.d[0], B.Hb, B.Hm[0]);
-    flow_terms<false>(Y4, Y6, -Y7, D.lam(2), D.rho(2), D.xt(2), vi, vj, vv, vj2, s, c, B.F[2], fb, B.gr, B.d[1], B.Hb, B.Hm[1]);
-    flow_terms<false>(-Y5, -Y7, -Y6, D.lam(3), D.rho(3), D.xt(3), vi, vj, vv, vj2, s, c, B.F[3], fb, B.gr, B.d[1], B.Hb, B.Hm[1]);
-    B.c[0] = EA_FMA(B.F[0], B.F[0], B.F[1] * B.F[1]) + x[4];
-    B.c[1] = EA_FMA(B.F[2], B.F[2], B.F[3] * B.F[3]) + x[5];
+    for (int j = 0; j < 2; ++j) {
+        const double a0 = mu * d[j][0], a1 = mu * d[j][1], a2 = mu * d[j][2];
+        H[0] = EA_FMA(a0, d[j][0], H[0]); H[1] = EA_FMA(a0, d[j][1], H[1]); H[2] = EA_FMA(a0, d[j][2], H[2]);
+        H[3] = EA_FMA(a1, d[j][1], H[3]); H[4] = EA_FMA(a1, d[j][2], H[4]); H[5] = EA_FMA(a2, d[j][2], H[5]);
+    }
     // consensus terms on w_i = vi^2, w_j = vj^2, t_i, t_j
     const double rho4 = D.rho(4), rho5 = D.rho(5), rho6 = D.rho(6), rho7 = D.rho(7);
     const double lam4 = D.lam(4), lam5 = D.lam(5), lam6 = D.lam(6), lam7 = D.lam(7);
     const double dwi = vi2 - D.xt(4), dwj = vj2 - D.xt(5), dti = x[2] - D.xt(6), dtj = x[3] - D.xt(7);
+    fv = EA_FMA(lam4, vi2, fv); fv = EA_FMA(0.5 * (rho4 * dwi), dwi, fv);
+    fv = EA_FMA(lam5, vj2, fv); fv = EA_FMA(0.5 * (rho5 * dwj), dwj, fv);
+    fv = EA_FMA(lam6, x[2], fv); fv = EA_FMA(0.5 * (rho6 * dti), dti, fv);
+    fv = EA_FMA(lam7, x[3], fv); fv = EA_FMA(0.5 * (rho7 * dtj), dtj, fv);
+    f = scale * fv;
     const double ri = EA_FMA(rho4, dwi, lam4), rj = EA_FMA(rho5, dwj, lam5);
-    fb = EA_FMA(lam4, vi2, fb); fb = EA_FMA(0.5 * (rho4 * dwi), dwi, fb);
-    fb = EA_FMA(lam5, vj2, fb); fb = EA_FMA(0.5 * (rho5 * dwj), dwj, fb);
-    fb = EA_FMA(lam6, x[2], fb); fb = EA_FMA(0.5 * (rho6 * dti), dti, fb);
-    fb = EA_FMA(lam7, x[3], fb); fb = EA_FMA(0.5 * (rho7 * dtj), dtj, fb);
-    B.fb = fb;
-    B.gr[0] = EA_FMA(2.0 * vi, ri, B.gr[0]);
-    B.gr[1] = EA_FMA(2.0 * vj, rj, B.gr[1]);
-    B.Hb[0] = EA_FMA(4.0 * rho4, vi2, EA_FMA(2.0, ri, B.Hb[0]));
-    B.Hb[3] = EA_FMA(4.0 * rho5, vj2, EA_FMA(2.0, rj, B.Hb[3]));
-    B.gt[0] = EA_FMA(rho6, dti, lam6);
-    B.gt[1] = EA_FMA(rho7, dtj, lam7);
-#endif
-}
-
-template <class View>
-EA_DEV void combine(const View &D, const Base &B, const double (&ls)[2], double mu, double scale,
-                    double &f, double (&g)[N], Sym6 &A) {
-#ifdef EA_PARITY
-    eval_fgh_ref(D, ls, mu, scale, B.x, f, g, A);
-#else
-    const double c0 = B.c[0], c1 = B.c[1];
-    const double m0 = EA_FMA(mu, c0, ls[0]), m1 = EA_FMA(mu, c1, ls[1]);
-    const double hm = 0.5 * mu;
-    f = scale * EA_FMA(hm * c1, c1, EA_FMA(hm * c0, c0, EA_FMA(ls[1], c1, EA_FMA(ls[0], c0, B.fb))));
-    double gy[3], a0[3], a1[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        gy[i] = EA_FMA(m1, B.d[1][i], EA_FMA(m0, B.d[0][i], B.gr[i]));
-        a0[i] = mu * B.d[0][i];
-        a1[i] = mu * B.d[1][i];
-    }
-    double H[6];
-    constexpr int ei[6] = { 0, 0, 0, 1, 1, 2 }, ej[6] = { 0, 1, 2, 1, 2, 2 };
-#pragma unroll
-    for (int e = 0; e < 6; ++e)
-        H[e] = EA_FMA(a1[ei[e]], B.d[1][ej[e]], EA_FMA(a0[ei[e]], B.d[0][ej[e]], EA_FMA(m1, B.Hm[1][e], EA_FMA(m0, B.Hm[0][e], B.Hb[e]))));
-    g[0] = scale * gy[0];
-    g[1] = scale * gy[1];
-    g[2] = scale * (gy[2] + B.gt[0]);
-    g[3] = scale * (B.gt[1] - gy[2]);
+    const double gy0 = EA_FMA(2.0 * vi, ri, EA_FMA(vj, Ps, (2.0 * As) * vi));
+    const double gy1 = EA_FMA(2.0 * vj, rj, EA_FMA(vi, Ps, (2.0 * Bs) * vj));
+    const double gy2 = vv * Qs;
+    H[0] = EA_FMA(4.0 * rho4, vi2, EA_FMA(2.0, ri, H[0]));
+    H[3] = EA_FMA(4.0 * rho5, vj2, EA_FMA(2.0, rj, H[3]));
+    g[0] = scale * gy0;
+    g[1] = scale * gy1;
+    g[2] = scale * (gy2 + EA_FMA(rho6, dti, lam6));
+    g[3] = scale * (EA_FMA(rho7, dtj, lam7) - gy2);
     g[4] = scale * m0;
     g[5] = scale * m1;
     using tron::tri;
@@ -325,36 +288,24 @@ EA_DEV void combine(const View &D, const Base &B, const double (&ls)[2], double 
     A.a[tri(1, 1)] = scale * H[3];
     A.a[tri(2, 0)] = h02;
     A.a[tri(2, 1)] = h12;
-    A.a[tri(2, 2)] = scale * (H[5] + D.rho(6));
+    A.a[tri(2, 2)] = scale * (H[5] + rho6);
     A.a[tri(3, 0)] = -h02;
     A.a[tri(3, 1)] = -h12;
     A.a[tri(3, 2)] = -h22;
-    A.a[tri(3, 3)] = scale * (H[5] + D.rho(7));
-    const double s02 = smu * B.d[0][2], s12 = smu * B.d[1][2];
-    A.a[tri(4, 0)] = smu * B.d[0][0];
-    A.a[tri(4, 1)] = smu * B.d[0][1];
+    A.a[tri(3, 3)] = scale * (H[5] + rho7);
+    const double s02 = smu * d[0][2], s12 = smu * d[1][2];
+    A.a[tri(4, 0)] = smu * d[0][0];
+    A.a[tri(4, 1)] = smu * d[0][1];
     A.a[tri(4, 2)] = s02;
     A.a[tri(4, 3)] = -s02;
     A.a[tri(4, 4)] = smu;
-    A.a[tri(5, 0)] = smu * B.d[1][0];
-    A.a[tri(5, 1)] = smu * B.d[1][1];
+    A.a[tri(5, 0)] = smu * d[1][0];
+    A.a[tri(5, 1)] = smu * d[1][1];
     A.a[tri(5, 2)] = s12;
     A.a[tri(5, 3)] = -s12;
     A.a[tri(5, 4)] = 0.0;
     A.a[tri(5, 5)] = smu;
 #endif
-}
-
-// Fused f, grad f, Hessian (packed lower) and the four flows F = (pij, qij, pji, qji)
-// (acopf_eval_linelimit_kernel_gpu.jl:17-22): a fresh evaluation = eval_base + combine.
-template <class View>
-EA_DEV void eval_fgh(const View &D, const double (&ls)[2], double mu, double scale,
-                     const double (&x)[N], double &f, double (&g)[N], Sym6 &A, double (&F)[4]) {
-    Base B;
-    eval_base(D, x, B);
-    combine(D, B, ls, mu, scale, f, g, A);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) F[k] = B.F[k];
 }
 
 // The branch objective bound to a data view (what the kernel and the harness plug into Lane).
@@ -506,11 +457,16 @@ EA_DEV void compute(Lane &L, const double (&xl)[N], const double (&xu)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) L.xc(i) = L.x[i];
     tron::Stats st;
-#ifdef EA_CAUCHY_LOOP
-    tron::compute_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st);
-#else
-    tron::compute_step_fast<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st);
+    // A branch past its first AL iteration is on the penalty ladder: its solves are Newton steps from a warm start, so the
+    // direct Newton step of tron.cuh is tried first (93 % success). First iterations take the literal algorithm alone:
+    // they run in full warps, where a failed attempt of one lane costs every lane the time of both paths. The rule
+    // depends on the branch's own history only, so a branch gives the same bits wherever and whenever it is solved.
+#ifndef EA_NEWTON_MODE
+#define EA_NEWTON_MODE 1
 #endif
+    const bool try_newton = (EA_NEWTON_MODE == 2) || (EA_NEWTON_MODE == 1 && L.it_al >= 1);
+    if (!(try_newton && tron::newton_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st)))
+        tron::compute_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st);
     L.cg += st.cg;
     L.shifts += st.shifts;
     L.phase = TRIAL;

@@ -188,11 +188,10 @@ int launch_x(ea_handle *h, long long major, int zsel, int max_auglag, double mu_
     if (!stream) stream = h->stream;
     build_pow_table(h, mu_max);
     if (major > 0 && lines)     // step-wise call: the fused loop resets the work queue itself (k_bus / k_ctrl_begin)
-        CK(cudaMemsetAsync(&h->d.ctrl->next_line, 0, 4 * sizeof(int), stream));      // next_line, q_head, q_tail (xq_reset)
+        CK(cudaMemsetAsync(&h->d.ctrl->next_line, 0, sizeof(int), stream));
     // persistent grid: as many CTAs as are resident at once, capped by the work available
     // one lane per branch at least: small grids are spread over all resident warps (k_xupdate: lanes_on)
-    const int bulk_warps = h->d.hand_al > 0 ? BULK_WARPS : XBLOCK / 32;
-    const int64_t work_blocks = std::max<int64_t>((h->nline + bulk_warps - 1) / bulk_warps, (h->ngen + XBLOCK - 1) / XBLOCK);
+    const int64_t work_blocks = std::max<int64_t>((h->nline + XBLOCK / 32 - 1) / (XBLOCK / 32), (h->ngen + XBLOCK - 1) / XBLOCK);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->x_resident_blocks, work_blocks));
     k_xupdate<<<grid, XBLOCK, XTILE_BYTES, stream>>>(h->d, h->pow_table, major, zsel, max_auglag, mu_max, scale, lines, gens);
     CK(cudaGetLastError());
@@ -383,7 +382,6 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
         if ((rc = dev_upload(h, const_cast<int **>(&d.br_from), brf))) return bail(rc);
         if ((rc = dev_upload(h, const_cast<int **>(&d.br_to), brt))) return bail(rc);
         if ((rc = dev_alloc(h, &d.als, 3 * (size_t)nline))) return bail(rc);       // membuf rows 25-27 start at 0 (acopf_model.jl:87-88)
-        if ((rc = dev_alloc(h, &d.chainq, (size_t)nline))) return bail(rc);        // chain queue of k_xupdate (ready flags start at 0)
     }
     lap("per-line data");
     {   // per generator slot
@@ -420,8 +418,6 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     if ((rc = dev_alloc(h, &h->res_dev, 4))) return bail(rc);
     if ((rc = dev_alloc(h, &h->staging, (size_t)std::max<int64_t>({ h->nvar, (int64_t)nline, (int64_t)nbus, (int64_t)ngen, 1 })))) return bail(rc);
     d.count_work = 1;
-    d.hand_al = 1;
-    d.chain_lanes = 16;
     d.nbus_active = nbus;
     h->n_owned_entries = nint;
     h->nvar_global = h->nvar;
@@ -959,10 +955,6 @@ int ea_set_option(ea_handle_t *h, const char *name, double value) {
     if (!strcmp(name, "chunk")) { h->default_chunk = std::max(1, (int)value); return EA_OK; }
     if (!strcmp(name, "kernel_timing")) { h->kernel_timing = value != 0.0; return EA_OK; }
     if (!strcmp(name, "use_graph")) { h->use_graph = value != 0.0; return EA_OK; }
-    // branch kernel: hand a branch over to the chain workers after this many AL iterations (0 = never: everything stays
-    // in the state machine), and how many lanes of a chain warp may hold a chain at a time
-    if (!strcmp(name, "hand_al")) { h->d.hand_al = std::max(0, (int)value); drop_loop_graph(h); return EA_OK; }
-    if (!strcmp(name, "chain_lanes")) { h->d.chain_lanes = std::min(32, std::max(1, (int)value)); drop_loop_graph(h); return EA_OK; }
     if (!strcmp(name, "l2_flush_mb")) {             // > 0: with kernel_timing, write this many MB before every iteration
         CK(cudaSetDevice(h->device));
         CK(cudaStreamSynchronize(h->stream));
@@ -1169,7 +1161,7 @@ int ea_diag_branch_eval(int device, int64_t n, const double *x, const double *pa
     return EA_OK;
 }
 
-int ea_diag_branch_solve(int device, int mode, int per_warp, int64_t n, const double *prob, int32_t max_auglag,
+int ea_diag_branch_solve(int device, int per_warp, int64_t n, const double *prob, int32_t max_auglag,
                          double mu_max, double scale, double *sol, int32_t *work, int64_t *cycles, double *kernel_ms) {
     ea_handle *h = nullptr;
     if (!prob || !sol || !work || !cycles || n < 0) return EA_ERR_ARG;
@@ -1182,20 +1174,14 @@ int ea_diag_branch_solve(int device, int mode, int per_warp, int64_t n, const do
     CK(cudaMalloc(&dp, 56 * n * sizeof(double))); CK(cudaMalloc(&ds, 13 * n * sizeof(double)));
     CK(cudaMalloc(&dw, 6 * n * sizeof(int))); CK(cudaMalloc(&dc, n * sizeof(long long)));
     CK(cudaMemcpy(dp, prob, 56 * n * sizeof(double), cudaMemcpyHostToDevice));
-    if (mode != 0 && mode != 1) return fail(h, EA_ERR_ARG, "ea_diag_branch_solve: mode must be 0 or 1");
-    CK(cudaFuncSetAttribute(k_diag_solve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, XTILE_BYTES));
-    CK(cudaFuncSetAttribute(k_diag_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, XTILE_BYTES));
+    CK(cudaFuncSetAttribute(k_diag_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, XTILE_BYTES));
     const int stride = per_warp ? 32 : 1;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; ++rep) {           // the second run is the timed one (instruction cache, clocks)
         CK(cudaEventRecord(e0));
-        if (mode == 0)
-            k_diag_solve<0><<<nblocks(n * stride, XBLOCK), XBLOCK, XTILE_BYTES>>>((int)n, stride, dp, tmp.pow_table, max_auglag,
-                                                                                 mu_max, scale, ds, dw, dc);
-        else
-            k_diag_solve<1><<<nblocks(n * stride, XBLOCK), XBLOCK, XTILE_BYTES>>>((int)n, stride, dp, tmp.pow_table, max_auglag,
-                                                                                 mu_max, scale, ds, dw, dc);
+        k_diag_solve<<<nblocks(n * stride, XBLOCK), XBLOCK, XTILE_BYTES>>>((int)n, stride, dp, tmp.pow_table, max_auglag, mu_max,
+                                                                          scale, ds, dw, dc);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
     }

@@ -16,7 +16,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "branch.cuh"
-#include "chain.cuh"
 
 namespace ea {
 
@@ -29,20 +28,8 @@ struct Ctrl {                 // device-resident loop control (one per handle)
     int done;                 // 1: primres <= eps_pri or inner == inner_limit; later launches are no-ops
     int zsel;                 // which of the two z buffers is z_curr
     unsigned ticket;          // last-block election for the residual reduction
+    int next_line;            // work queue head of the branch kernel (reset for the next x-update)
     unsigned long long seq;   // partitioned iterations executed since the handle was created (exchange stamps / parity)
-    // work queues of the branch kernel, reset together for the next x-update (xq_reset)
-    int next_line;            // head of the branch queue
-    int q_head, q_tail;       // chain queue (branches handed over after their first AL iteration): claimed / pushed
-    int xq_pad;
-};
-__device__ __forceinline__ void xq_reset(Ctrl *c) { c->next_line = 0; c->q_head = 0; c->q_tail = 0; }
-
-// One entry of the chain queue: the state of a branch after an augmented-Lagrangian update (chain::State) and its index.
-// `ready` is raised by the pusher after the payload (st.release) and cleared by the consumer.
-struct __align__(16) QEntry {
-    double x[6], ls[2], mu, eta;
-    int I, it_al, evals, cg, shifts, rejected, hit_max;
-    unsigned ready;
 };
 
 struct Counters { unsigned long long v[8]; unsigned long long t[4]; };   // t: first start, queue empty, last end (globaltimer ns), launches
@@ -57,9 +44,6 @@ struct Dev {                  // everything the kernels need, passed by value
     const double *xlu;                    // 8 x nline: xl0,xu0,xl1,xu1,xl2,xu2,xl3,xu3
     const double *rateA;                  // nline
     double *als;                          // 3 x nline: lambda_s1, lambda_s2, mu   (membuf rows 25-27)
-    QEntry *chainq;                       // nline entries: the chain queue of k_xupdate
-    int hand_al;                          // hand a branch over to the chain workers after this many AL iterations (0: never)
-    int chain_lanes;                      // live lanes per chain warp (fewer lanes = less divergence per round)
     const int *br_from, *br_to;           // bus of each end (init_solution only)
     // per generator slot (SoA, ngen each)
     const double *pgmin_curr, *pgmax_curr, *qgmin, *qgmax, *c2, *c1, *pgmin, *pgmax;
@@ -245,16 +229,16 @@ __device__ __forceinline__ void generator_update(const Dev &d, const double *z, 
     *reinterpret_cast<double2 *>(d.u + 2 * k) = u;
 }
 
-// Stage the inputs of branch I into the lane's tile column (auglag_gpu.jl:50-73; rows of branch::TileView).
-// Returns the previous u of the two ends (the start point is made from it).
-__device__ __forceinline__ void stage_branch(const Dev &d, const double *z, int I, double *col, d4 &uf, d4 &ut) {
+// Stage branch I into the lane's tile column and set the start point (auglag_gpu.jl:23-80).
+__device__ __forceinline__ void load_branch(const Dev &d, const double *z, int I, long long major, double *col,
+                                            branch::Lane &L) {
     const int nl = d.nline;
     const int sf = d.slot_from[I], st = d.slot_to[I];
     const double *uh = d.u + d.gpad, *vh = d.v + d.gpad, *zh = z + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
     const d4 lf = ld4(lh, sf), lt = ld4(lh, st);
     const d4 rf = ld4(rh, sf), rt = ld4(rh, st);
     const d4 vf = ld4(vh, sf), vt = ld4(vh, st), zf = ld4(zh, sf), zt = ld4(zh, st);
-    uf = ld4(uh, sf); ut = ld4(uh, st);
+    const d4 uf = ld4(uh, sf), ut = ld4(uh, st);
     const double lam[8] = { lf.p, lf.q, lt.p, lt.q, lf.w, lt.w, lf.t, lt.t };
     const double rho[8] = { rf.p, rf.q, rt.p, rt.q, rf.w, rt.w, rf.t, rt.t };
     const double xt[8] = { vf.p - zf.p, vf.q - zf.q, vt.p - zt.p, vt.q - zt.q, vf.w - zf.w, vt.w - zt.w, vf.t - zf.t, vt.t - zt.t };
@@ -264,21 +248,12 @@ __device__ __forceinline__ void stage_branch(const Dev &d, const double *z, int 
         col[(8 + k) * XBLOCK] = rho[k];
         col[(16 + k) * XBLOCK] = xt[k];
         col[(24 + k) * XBLOCK] = d.Y[k * nl + I];
-        col[(32 + k) * XBLOCK] = d.xlu[k * nl + I];
     }
-    col[40 * XBLOCK] = d.rateA[I];
-}
-
-// Stage branch I and set the start point (auglag_gpu.jl:23-80).
-__device__ __forceinline__ void load_branch(const Dev &d, const double *z, int I, long long major, double *col,
-                                            branch::Lane &L) {
-    const int nl = d.nline;
-    d4 uf, ut;
-    stage_branch(d, z, I, col, uf, ut);
     double b[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) b[k] = col[(32 + k) * XBLOCK];
-    const double ra = col[40 * XBLOCK];
+    for (int k = 0; k < 8; ++k) { b[k] = d.xlu[k * nl + I]; col[(32 + k) * XBLOCK] = b[k]; }
+    const double ra = d.rateA[I];
+    col[40 * XBLOCK] = ra;
     // start point from the previous u (auglag_gpu.jl:43-48); b = xl0,xu0,xl1,xu1,...
     L.x[0] = fmin(b[1], fmax(b[0], sqrt(uf.w)));
     L.x[1] = fmin(b[3], fmax(b[2], sqrt(ut.w)));
@@ -299,97 +274,20 @@ __device__ __forceinline__ void load_bounds(const double *col, double (&xl)[6], 
 }
 
 // Write back u and the AL state of a finished branch (auglag_gpu.jl:135-145).
-__device__ __forceinline__ void store_result(const Dev &d, int I, const double (&x)[6], const double (&F)[4],
-                                             double ls0, double ls1, double mu) {
+__device__ __forceinline__ void store_branch(const Dev &d, int I, const branch::Lane &L) {
     const int nl = d.nline;
     d4 of, ot;
-    of.p = F[0]; of.q = F[1]; of.w = x[0] * x[0]; of.t = x[2];
-    ot.p = F[2]; ot.q = F[3]; ot.w = x[1] * x[1]; ot.t = x[3];
+    of.p = L.Fc(0); of.q = L.Fc(1); of.w = L.x[0] * L.x[0]; of.t = L.x[2];
+    ot.p = L.Fc(2); ot.q = L.Fc(3); ot.w = L.x[1] * L.x[1]; ot.t = L.x[3];
     st4(d.u + d.gpad, d.slot_from[I], of);
     st4(d.u + d.gpad, d.slot_to[I], ot);
-    d.als[I] = ls0; d.als[nl + I] = ls1; d.als[2 * nl + I] = mu;
+    d.als[I] = L.ls[0]; d.als[nl + I] = L.ls[1]; d.als[2 * nl + I] = L.mu;
 }
-__device__ __forceinline__ void store_branch(const Dev &d, int I, const branch::Lane &L) {
-    const double F[4] = { L.Fc(0), L.Fc(1), L.Fc(2), L.Fc(3) };
-    store_result(d, I, L.x, F, L.ls[0], L.ls[1], L.mu);
-}
-
-// ---- chain queue -------------------------------------------------------------------------------------------
-// Hand-over of a branch whose AL loop continues. Pushers reserve a slot with an atomic on q_tail, write the payload
-// and raise `ready` with a release store; consumers claim slots [q_head, q_tail) with a compare-and-swap (never more
-// than have been reserved), wait for `ready`, read the payload past the L1 and clear the flag for the next launch.
-// No worker ever waits for a CTA that might not be resident: the only wait is for a pusher between its reservation
-// and its release store. Every warp drains the queue before it retires, so an entry pushed late is solved by its own
-// pusher at the latest.
-__device__ __forceinline__ void chain_push(const Dev &d, int I, const branch::Lane &L, bool mine) {
-    const unsigned full = 0xffffffffu;
-    const unsigned m = __ballot_sync(full, mine);
-    if (!m) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&d.ctrl->q_tail, __popc(m));
-    base = __shfl_sync(full, base, leader);
-    if (!mine) return;
-    QEntry *e = d.chainq + base + __popc(m & ((1u << lane) - 1u));
-#pragma unroll
-    for (int i = 0; i < 6; ++i) e->x[i] = L.x[i];
-    e->ls[0] = L.ls[0]; e->ls[1] = L.ls[1]; e->mu = L.mu; e->eta = L.eta();
-    e->I = I; e->it_al = L.it_al; e->evals = L.evals; e->cg = L.cg; e->shifts = L.shifts; e->rejected = L.rejected;
-    e->hit_max = L.hit_max;
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(&e->ready), "r"(1u) : "memory");
-}
-
-// Claim up to `want` entries for the warp (leader lane does the CAS); returns the first claimed slot, count in `got`.
-__device__ __forceinline__ int chain_claim(const Dev &d, int want, int &got) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    int first = 0, n = 0;
-    if (lane == 0 && want > 0) {
-        volatile int *qh = &d.ctrl->q_head, *qt = &d.ctrl->q_tail;
-        for (;;) {
-            const int h = *qh, t = *qt;
-            n = min(want, t - h);
-            if (n <= 0) { n = 0; break; }
-            if (atomicCAS(&d.ctrl->q_head, h, h + n) == h) { first = h; break; }
-        }
-    }
-    got = __shfl_sync(full, n, 0);
-    return __shfl_sync(full, first, 0);
-}
-
-__device__ __forceinline__ void chain_pop(const Dev &d, int slot, chain::State &S, int &I) {
-    QEntry *e = d.chainq + slot;
-    unsigned r;
-    do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(&e->ready) : "memory"); } while (r == 0u);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) S.x[i] = __ldcg(&e->x[i]);
-    S.ls[0] = __ldcg(&e->ls[0]); S.ls[1] = __ldcg(&e->ls[1]); S.mu = __ldcg(&e->mu); S.eta = __ldcg(&e->eta);
-    I = __ldcg(&e->I); S.it_al = __ldcg(&e->it_al); S.evals = __ldcg(&e->evals); S.cg = __ldcg(&e->cg);
-    S.shifts = __ldcg(&e->shifts); S.rejected = __ldcg(&e->rejected); S.hit_max = __ldcg(&e->hit_max);
-    e->ready = 0u;
-}
-
-// ---------------------------------------------------------------------------
-// k_xupdate. Persistent grid (the CTAs resident at once), 4 warps per CTA in two roles:
-//   bulk warps   (BULK_WARPS of them) run the state machine of branch.cuh over the branch queue (ctrl->next_line): one
-//                lane per branch at a time, refilled as branches finish. A branch whose AL loop does not end with its
-//                first iteration (4 % of the branches, 15-20 % of the evaluations, and ALL of the long serial chains)
-//                is pushed to the chain queue instead of being continued.
-//   chain warps  run chain::al_iteration (chain.cuh) on the handed-over branches, one branch per lane, at most
-//                d.chain_lanes lanes live per warp, refilled at AL-iteration boundaries: they start on a chain
-//                within microseconds of its detection instead of after the bulk has drained. Bulk warps join them
-//                once the branch queue is empty.
-// ---------------------------------------------------------------------------
-#ifndef EA_BULK_WARPS
-#define EA_BULK_WARPS 3
-#endif
-constexpr int BULK_WARPS = EA_BULK_WARPS;
 
 __global__ void __launch_bounds__(XBLOCK, EA_XMINB)
 k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_auglag, double mu_max, double scale,
           int do_lines, int do_gens) {
     extern __shared__ double tile[];                       // TILE_ROWS x XBLOCK
-    __shared__ int bulk_warps_left;
     long long major = major_arg;
     int zsel = zsel_arg;
     if (major_arg == 0) {
@@ -402,137 +300,69 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
         for (int k = blockIdx.x * XBLOCK + threadIdx.x; k < d.ngen; k += gridDim.x * XBLOCK) generator_update(d, z, k);
     if (!do_lines) return;
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const bool handover = d.hand_al > 0;
-    const int n_bulk = handover ? BULK_WARPS : XBLOCK / 32;
-    if (threadIdx.x == 0) bulk_warps_left = n_bulk;
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
     unsigned long long t_now = 0;
     if (d.count_work > 1 && threadIdx.x == 0) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
         atomicMin(&d.counters->t[0], t_now);
     }
+    bool saw_empty = false;
     double *col = tile + threadIdx.x;
+    const branch::Objective<branch::TileView<XBLOCK>> eval{ { col }, scale };
+    branch::Lane L;
+    L.cold = tile + branch::TILE_COLD * XBLOCK + threadIdx.x; L.cs = XBLOCK;
+    // Small grids: fewer lanes per warp, more warps. A round of the state machine costs a warp ~14 us when its 32 lanes
+    // sit in different phases of different branches, ~7.5 us when only a few lanes are live; with fewer branches than
+    // resident lanes the work is spread over all warps instead of filling the first ones.
+    const int lanes_on = min(32, max(1, (d.nline + gridDim.x * (XBLOCK / 32) - 1) / (gridDim.x * (XBLOCK / 32))));
+    L.phase = (lane < lanes_on) ? branch::NEED : branch::DONE;
+    L.step_pending = false;
+    int I = -1;
     unsigned work[7] = { 0, 0, 0, 0, 0, 0, 0 };            // calls, auglag, evals, cg, shifts, rejected, hit_max (per lane: 32 bits)
     int mx = 0;
 
-    if (wid < n_bulk) {
-        // ================= bulk role: the state machine over the branch queue =================
-        bool saw_empty = false;
-        const branch::Objective<branch::TileView<XBLOCK>> eval{ { col }, scale };
-        branch::Lane L;
-        L.cold = tile + branch::TILE_COLD * XBLOCK + threadIdx.x; L.cs = XBLOCK;
-        // Small grids: fewer lanes per warp, more warps. A round of the state machine costs a warp ~14 us when its 32 lanes
-        // sit in different phases of different branches, ~7.5 us when only a few lanes are live; with fewer branches than
-        // resident lanes the work is spread over all warps instead of filling the first ones.
-        const int lanes_on = min(32, max(1, (d.nline + gridDim.x * n_bulk - 1) / (gridDim.x * n_bulk)));
-        L.phase = (lane < lanes_on) ? branch::NEED : branch::DONE;
-        L.step_pending = false;
-        int I = -1;
 #pragma unroll 1
-        for (;;) {
+    for (;;) {
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                // refill: lanes without a branch take the next ones from the queue
-                const bool need = (L.phase == branch::NEED);
-                const unsigned m = __ballot_sync(full, need);
-                if (m) {
-                    int base = 0;
-                    if (lane == __ffs(m) - 1) base = atomicAdd(&d.ctrl->next_line, __popc(m));
-                    base = __shfl_sync(full, base, __ffs(m) - 1);
-                    if (need) {
-                        I = base + __popc(m & ((1u << lane) - 1u));
-                        if (I < d.nline) { load_branch(d, z, I, major, col, L); branch::begin(L, T); }
-                        else {
-                            L.phase = branch::DONE;
-                            if (d.count_work > 1 && !saw_empty) {
-                                saw_empty = true;
-                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-                                atomicMin(&d.counters->t[1], t_now);
-                            }
+        for (int pass = 0; pass < 2; ++pass) {
+            // refill: lanes without a branch take the next ones from the queue
+            const bool need = (L.phase == branch::NEED);
+            const unsigned m = __ballot_sync(full, need);
+            if (m) {
+                int base = 0;
+                if (lane == __ffs(m) - 1) base = atomicAdd(&d.ctrl->next_line, __popc(m));
+                base = __shfl_sync(full, base, __ffs(m) - 1);
+                if (need) {
+                    I = base + __popc(m & ((1u << lane) - 1u));
+                    if (I < d.nline) { load_branch(d, z, I, major, col, L); branch::begin(L, T); }
+                    else {
+                        L.phase = branch::DONE;
+                        if (d.count_work > 1 && !saw_empty) {
+                            saw_empty = true;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                            atomicMin(&d.counters->t[1], t_now);
                         }
                     }
                 }
-                double xl[6], xu[6];
-                load_bounds(col, xl, xu);
-                if (branch::eval_pass(L, eval, pass, xl, xu, max_auglag, mu_max, T)) {
-                    store_branch(d, I, L);
-                    work[0] += 1; work[1] += L.it_al; work[2] += L.evals; work[3] += L.cg; work[4] += L.shifts;
-                    work[5] += L.rejected; work[6] += L.hit_max;
-                    mx = max(mx, L.evals);
-                    L.phase = branch::NEED;
-                }
-                if (handover && pass == 0) {
-                    // the AL loop of this branch goes on (eval_pass left it at START with it_al AL updates done): hand it over
-                    const bool give = (L.phase == branch::START) && (L.it_al >= d.hand_al);
-                    chain_push(d, I, L, give);
-                    if (give) L.phase = branch::NEED;
-                }
-            }
-            if (__all_sync(full, L.phase == branch::DONE || L.phase == branch::NEED)) {
-                // NEED here means "finished in pass 1" cannot happen (pass 1 never finishes); lanes that finished in
-                // pass 0 were refilled or retired at the top of pass 1, so all lanes are DONE.
-                if (__all_sync(full, L.phase == branch::DONE)) break;
             }
             double xl[6], xu[6];
             load_bounds(col, xl, xu);
-            branch::compute(L, xl, xu);
-        }
-        if (lane == 0) atomicSub(&bulk_warps_left, 1);
-    }
-
-    if (handover) {
-        // ================= chain role =================
-        const branch::TileView<XBLOCK> D{ col };
-        chain::State S;
-        double f = 0.0, g[6], Fc[4];
-        branch::Sym6 A;
-        int I = -1;
-        bool have = false;
-        const int cl = max(1, min(32, d.chain_lanes));
-        volatile int *left = &bulk_warps_left;
-#pragma unroll 1
-        for (;;) {
-            // refill at an AL-iteration boundary
-            const unsigned live = __ballot_sync(full, have);
-            const int want = min(cl - __popc(live), 4);
-            int got = 0;
-            const int first = chain_claim(d, want, got);
-            if (got > 0) {
-                const unsigned idle = ~live;
-                const int rank = __popc(idle & ((1u << lane) - 1u));       // my index among the idle lanes
-                if (!have && rank < got) {
-                    chain_pop(d, first + rank, S, I);
-                    d4 uf, ut;
-                    stage_branch(d, z, I, col, uf, ut);
-                    chain::start_eval(D, scale, S, f, g, A, Fc);
-                    have = true;
-                }
-            } else if (!live) {
-                // nothing to do: retire once no branch can arrive any more from this CTA's point of view (branch queue
-                // drained, our own bulk warps done) - a late push elsewhere is solved by its pusher. One lane decides
-                // for the warp (the lanes would read the counters at different times).
-                int quit = 0;
-                if (lane == 0) {
-                    volatile int *nx = &d.ctrl->next_line, *qh = &d.ctrl->q_head, *qt = &d.ctrl->q_tail;
-                    if (*nx >= d.nline && *left == 0) quit = (*qh >= *qt);
-                    else __nanosleep(256);
-                }
-                if (__shfl_sync(full, quit, 0)) break;
-                continue;
-            }
-            if (have) {
-                double xl[6], xu[6];
-                load_bounds(col, xl, xu);
-                if (chain::al_iteration(D, scale, xl, xu, S, f, g, A, Fc, max_auglag, mu_max, T)) {
-                    store_result(d, I, S.x, Fc, S.ls[0], S.ls[1], S.mu);
-                    work[0] += 1; work[1] += S.it_al; work[2] += S.evals; work[3] += S.cg; work[4] += S.shifts;
-                    work[5] += S.rejected; work[6] += S.hit_max;
-                    mx = max(mx, S.evals);
-                    have = false;
-                }
+            if (branch::eval_pass(L, eval, pass, xl, xu, max_auglag, mu_max, T)) {
+                store_branch(d, I, L);
+                work[0] += 1; work[1] += L.it_al; work[2] += L.evals; work[3] += L.cg; work[4] += L.shifts;
+                work[5] += L.rejected; work[6] += L.hit_max;
+                mx = max(mx, L.evals);
+                L.phase = branch::NEED;
             }
         }
+        if (__all_sync(full, L.phase == branch::DONE || L.phase == branch::NEED)) {
+            // NEED here means "finished in pass 1" cannot happen (pass 1 never finishes); lanes that finished in
+            // pass 0 were refilled or retired at the top of pass 1, so all lanes are DONE.
+            if (__all_sync(full, L.phase == branch::DONE)) break;
+        }
+        double xl[6], xu[6];
+        load_bounds(col, xl, xu);
+        branch::compute(L, xl, xu);
     }
 
     if (d.count_work > 1 && lane == 0) {
@@ -821,7 +651,7 @@ __device__ __forceinline__ void bus_body(const Dev &d, int zsel_arg, double beta
             const long long inner = c->inner + 1;
             c->inner = inner;
             c->zsel = zsel ^ 1;
-            xq_reset(c);
+            c->next_line = 0;
             // admm_two_level.jl:60-62 and the `while inner < inner_iterlim` bound (:34)
             if (c->res[0] <= c->eps_pri || inner >= c->inner_limit) c->done = 1;
         }
@@ -896,7 +726,7 @@ __global__ void __launch_bounds__(FBLOCK) k_finish(Dev d) {
         const long long inner = c->inner + 1;
         c->inner = inner;
         c->zsel = zsel ^ 1;
-        xq_reset(c);
+        c->next_line = 0;
         c->seq = seq + 1ull;
         if (c->res[0] <= c->eps_pri || inner >= c->inner_limit) c->done = 1;
     }
@@ -976,9 +806,8 @@ __global__ void k_membuf_row(Dev d, int zsel, int row, double *out) {
 
 __global__ void k_ctrl_begin(Ctrl *c, double beta, double eps_pri, long long inner0, long long inner_limit, int zsel) {
     c->beta = beta; c->eps_pri = eps_pri; c->inner = inner0; c->inner_limit = inner_limit;
-    c->done = 0; c->zsel = zsel; c->ticket = 0u; xq_reset(c);
+    c->done = 0; c->zsel = zsel; c->ticket = 0u; c->next_line = 0;
 }
-__global__ void k_xq_reset(Ctrl *c) { xq_reset(c); }
 
 // diagnostics: evaluate f, g, H for a batch of points (unit parity vs the oracle)
 __global__ void k_diag_eval(int n, const double *x, const double *param, const double *Y, double scale,
@@ -1007,8 +836,7 @@ __global__ void k_diag_eval(int n, const double *x, const double *param, const d
 // diagnostics / tests: solve a batch of branch sub-problems with one of the two drivers, outside the ADMM loop.
 // prob: n x 56 (tests/golden/hard_branches.npz: lam8 rho8 xt8 Y8 | xl6 xu6 | x0(6) | ls0 ls1 mu | major rateA pad),
 // sol: n x 13 (x6 F4 ls0 ls1 mu), work: n x 6, cyc: n (SM cycles of the solve).
-// mode bit 0: 0 = state machine (branch::solve), 1 = chain driver; `stride` = 1: one problem per lane, 32: one per warp.
-template <int MODE>
+// `stride` = 1: one problem per lane, 32: one per warp (a lone lane: the regime of the kernel's tail).
 __global__ void __launch_bounds__(XBLOCK, EA_XMINB)
 k_diag_solve(int n, int stride, const double *prob, branch::PowTable T, int max_auglag, double mu_max,
              double scale, double *sol, int *work, long long *cyc) {
@@ -1027,32 +855,27 @@ k_diag_solve(int n, int stride, const double *prob, branch::PowTable T, int max_
     int w[6];
     long long t0, t1;
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0));
-    if (MODE & 1) {
-        chain::State S;
+    branch::Lane L;
+    L.cold = tile + branch::TILE_COLD * XBLOCK + threadIdx.x; L.cs = XBLOCK;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) S.x[k] = x[k];
-        S.ls[0] = p[50]; S.ls[1] = p[51]; S.mu = p[52];
-        chain::init_state(S, T);
-        chain::solve(D, scale, xl, xu, S, F, max_auglag, mu_max, T);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) x[k] = S.x[k];
-        ls0 = S.ls[0]; ls1 = S.ls[1]; mu = S.mu;
-        w[0] = S.it_al; w[1] = S.evals; w[2] = S.cg; w[3] = S.shifts; w[4] = S.rejected; w[5] = S.hit_max;
-    } else {
-        branch::Lane L;
-        L.cold = tile + branch::TILE_COLD * XBLOCK + threadIdx.x; L.cs = XBLOCK;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) L.x[k] = x[k];
-        L.ls[0] = p[50]; L.ls[1] = p[51]; L.mu = p[52];
-        const branch::Objective<branch::TileView<XBLOCK>> eval{ D, scale };
-        branch::solve(L, eval, xl, xu, max_auglag, mu_max, T);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) x[k] = L.x[k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) F[k] = L.Fc(k);
-        ls0 = L.ls[0]; ls1 = L.ls[1]; mu = L.mu;
-        w[0] = L.it_al; w[1] = L.evals; w[2] = L.cg; w[3] = L.shifts; w[4] = L.rejected; w[5] = L.hit_max;
+    for (int k = 0; k < 6; ++k) L.x[k] = x[k];
+    L.ls[0] = p[50]; L.ls[1] = p[51]; L.mu = p[52];
+    const branch::Objective<branch::TileView<XBLOCK>> eval{ D, scale };
+    branch::begin(L, T);
+    bool fin = false;
+#pragma unroll 1
+    while (!fin) {                      // the loop of k_xupdate for one lane: one evaluation site serves both passes
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass)
+            if (branch::eval_pass(L, eval, pass, xl, xu, max_auglag, mu_max, T)) { fin = true; break; }
+        if (!fin) branch::compute(L, xl, xu);
     }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x[k] = L.x[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) F[k] = L.Fc(k);
+    ls0 = L.ls[0]; ls1 = L.ls[1]; mu = L.mu;
+    w[0] = L.it_al; w[1] = L.evals; w[2] = L.cg; w[3] = L.shifts; w[4] = L.rejected; w[5] = L.hit_max;
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1));
     double *o = sol + 13 * (size_t)i;
 #pragma unroll

@@ -240,13 +240,13 @@ __global__ void __launch_bounds__(MP_FIN_BLOCK) k_mp_finish(MpDev m) {
     __syncthreads();
     for (int t = threadIdx.x; t < m.T; t += MP_FIN_BLOCK) {
         Ctrl *p = m.pctrl[t];
-        p->inner = s_inner; p->zsel = zsel ^ 1; xq_reset(p); p->done = s_done;
+        p->inner = s_inner; p->zsel = zsel ^ 1; p->next_line = 0; p->done = s_done;
     }
     if (threadIdx.x == 0) {
         c->inner = s_inner;
         c->zsel = zsel ^ 1;
         c->done = s_done;
-        xq_reset(c);
+        c->next_line = 0;
         *m.ticket = 0u;
     }
 }
@@ -256,7 +256,7 @@ __global__ void k_mp_ctrl_begin(MpDev m, double beta, double eps_pri, long long 
     if (t > m.T) return;
     Ctrl *c = (t == m.T) ? m.ctrl : m.pctrl[t];
     c->beta = beta; c->eps_pri = eps_pri; c->inner = inner0; c->inner_limit = inner_limit;
-    c->done = 0; c->zsel = zsel; c->ticket = 0u; xq_reset(c);
+    c->done = 0; c->zsel = zsel; c->ticket = 0u; c->next_line = 0;
     if (t == m.T) *m.ticket = 0u;
 }
 

@@ -248,88 +248,6 @@ template <int N> EA_DEV double cauchy(const double (&x)[N], const double (&xl)[N
     return alpha;
 }
 
-// Cauchy step with the search done in closed form on the straight part of the projected path. Up to the first break
-// point the projected step is s(alpha) = -alpha * gh with gh = g on the variables that can move and 0 on those held
-// by a bound, so |s| = alpha |gh|, g's = -alpha gh'gh and q(s) = alpha (alpha/2 gh'A gh - gh'gh): one matrix-vector
-// product serves every trial of the search (the original does a projected step, a norm and a quadratic form per
-// trial). Trials beyond the first break point take the general formulas. Same decisions as cauchy() except where a
-// comparison is within rounding of a tie (the values differ in the last bits); the exact tie |s(1)| = delta = |g| of
-// a START is preserved. EA_EXACT builds (parity build, host harness vs the oracle) keep the literal algorithm.
-template <int N> EA_DEV double cauchy_straight(const double (&x)[N], const double (&xl)[N], const double (&xu)[N],
-                                               const Sym<N> &A, const double (&g)[N], double delta, double alpha,
-                                               double (&s)[N]) {
-#if EA_EXACT
-    return cauchy<N>(x, xl, xu, A, g, delta, alpha, s);
-#else
-    const double mu0 = 0.01, interpf = 0.1, extrapf = 10.0;
-    double gh[N], bp[N];
-    bool has[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const double wi = -g[i];
-        const bool up = (x[i] < xu[i]) && (wi > 0.0);
-        const bool dn = (x[i] > xl[i]) && (wi < 0.0);
-        has[i] = up || dn;
-        bp[i] = ddiv((up ? xu[i] : xl[i]) - x[i], has[i] ? wi : 1.0);
-        gh[i] = has[i] ? g[i] : 0.0;
-    }
-    bool any = false;
-    double brptmin = 0.0, brptmax = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const double lo = any ? dmin(brptmin, bp[i]) : bp[i];
-        const double hi = any ? dmax(brptmax, bp[i]) : bp[i];
-        brptmin = has[i] ? lo : brptmin;
-        brptmax = has[i] ? hi : brptmax;
-        any = any || has[i];
-    }
-    double Ag[N];
-    symv<N>(A, gh, Ag);
-    const double gg = dot<N>(gh, gh), gAg = dot<N>(gh, Ag);
-    const double gnorm = dsqrt(gg);
-    int mode = 0;
-    double alphas = alpha;
-#pragma unroll 1
-    while (mode != 4) {
-        if (mode == 3) break;
-        bool within;
-        double q, gts;
-        if (alpha <= brptmin) {
-            within = alpha * gnorm <= delta;
-            gts = -(alpha * gg);
-            q = alpha * EA_FMA(0.5 * alpha, gAg, -gg);
-        } else {
-            gpstep<N>(x, xl, xu, -alpha, g, s);
-            within = nrm2<N>(s) <= delta;
-            quad<N>(A, g, s, q, gts);
-        }
-        if (mode == 0) {
-            const bool interp = !within || (q >= mu0 * gts);
-            if (interp) { mode = 1; alpha = interpf * alpha; }
-            else {
-                alphas = alpha;
-                if (alpha <= brptmax) { mode = 2; alpha = extrapf * alpha; }
-                else mode = 3;
-            }
-        } else if (mode == 1) {
-            if (within && !(q > mu0 * gts)) mode = 4;
-            else alpha = interpf * alpha;
-        } else {
-            bool search = true;
-            if (within) { if (q < mu0 * gts) alphas = alpha; }
-            else search = false;
-            if (search && alpha <= brptmax) alpha = extrapf * alpha;
-            else { alpha = alphas; mode = 3; }
-        }
-    }
-    if (alpha <= brptmin) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) s[i] = -alpha * gh[i];
-    } else gpstep<N>(x, xl, xu, -alpha, g, s);
-    return alpha;
-#endif
-}
-
 // Lower-triangular solves with the free-set mask folded into L (fixed rows are e_i).
 template <int N> EA_DEV void lsolve(const Chol<N> &L, double (&r)[N]) {      // L r = b
 #pragma unroll
@@ -676,7 +594,7 @@ template <int N> EA_DEV bool chol_masked(const Sym<N> &A, unsigned freemask, Cho
 // that outcome directly - the Cauchy scalars, one Cholesky factorization, two triangular solves - and verifies every
 // condition the literal algorithm would have tested on the way (trust region in the preconditioned norm, bounds,
 // residual of the face). If any of them fails it returns false WITHOUT touching its arguments and the caller runs the
-// literal algorithm (compute_step_fast). Results agree with the literal path to rounding (the step is the same
+// literal algorithm (compute_step). Results agree with the literal path to rounding (the step is the same
 // vector computed with fewer operations), decisions except within rounding of a tie; EA_EXACT builds never take it.
 template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
                                          const Sym<N> &A, const double (&g)[N], double delta,
@@ -685,7 +603,9 @@ template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], 
     return false;
 #else
     const double mu0 = 0.01, interpf = 0.1, extrapf = 10.0, cgtol = 0.1;
-    // ---- Cauchy search on the straight part (cauchy_straight) ----
+    // ---- Cauchy search in closed form on the straight part of the projected path: up to the first break point the
+    // projected step is s(alpha) = -alpha gh (gh = g on the variables that can move, 0 on those held by a bound), so
+    // |s| = alpha |gh|, g's = -alpha gh'gh, q(s) = alpha (alpha/2 gh'A gh - gh'gh): the trials of dcauchy are scalar ----
     double gh[N], bp[N];
     bool has[N];
 #pragma unroll
@@ -800,22 +720,6 @@ template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], 
     st.cg += 1;
     return true;
 #endif
-}
-
-// compute_step with the closed-form Cauchy search (chain.cuh)
-template <int N> EA_DEV void compute_step_fast(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
-                                               const Sym<N> &A, const double (&g)[N], double delta,
-                                               double &alphac, double &prered, double &gts, double &snorm,
-                                               Stats &st) {
-    if (newton_step<N>(x, xl, xu, A, g, delta, alphac, prered, gts, snorm, st)) return;
-    const double cgtol = 0.1;
-    double s[N];
-    alphac = cauchy_straight<N>(x, xl, xu, A, g, delta, alphac, s);
-    spcg<N>(x, xl, xu, A, g, delta, cgtol, s, N, st);
-    double q;
-    quad<N>(A, g, s, q, gts);
-    prered = -q;
-    snorm = nrm2<N>(s);
 }
 
 // The "EVALUATE" part of dtron (B.0): trust-region update and acceptance.

@@ -404,11 +404,11 @@ int  ea_diag_branch_eval(int device, int64_t n, const double *x, const double *p
 
 /* Diagnostics: measured FP64 FMA throughput of the device in TFLOP/s (8 independent
  * DFMA chains per thread, best of 5); the roofline denominator of the branch kernel. */
-/* Solve n branch sub-problems outside the ADMM loop with one of the two drivers of k_xupdate (mode 0: the state
- * machine of branch.cuh, 1: the chain driver of chain.cuh), one problem per lane or (per_warp) one per warp.
+/* Solve n branch sub-problems outside the ADMM loop with the branch driver of k_xupdate (the state machine of
+ * branch.cuh), one problem per lane or (per_warp) one per warp - a lone lane, the regime of the kernel's tail.
  * prob: n x 56 doubles (layout of tests/golden/hard_branches.npz), sol: n x 13, work: n x 6, cycles: n SM cycles.
- * Tests (the drivers agree bit for bit, and with the host build of the same code) and latency probes. */
-int  ea_diag_branch_solve(int device, int mode, int per_warp, int64_t n, const double *prob, int32_t max_auglag,
+ * Tests (device = host build of the same code on the hardest branches of a real solve) and latency probes. */
+int  ea_diag_branch_solve(int device, int per_warp, int64_t n, const double *prob, int32_t max_auglag,
                           double mu_max, double scale, double *sol, int32_t *work, int64_t *cycles, double *kernel_ms);
 int  ea_diag_fp64_peak(int device, double *tflops);
 

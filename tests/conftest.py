@@ -62,8 +62,6 @@ def _load_harness(name):
     pd = C.POINTER(C.c_double)
     H.hh_solve_branch.argtypes = [pd, pd, pd, pd, pd, C.c_longlong, C.c_int, C.c_double, C.c_double, pd,
                                   C.POINTER(C.c_int)]
-    H.hh_solve_chain.argtypes = [pd, pd, pd, pd, pd, C.c_longlong, C.c_int, C.c_double, C.c_double, C.c_int, pd,
-                                 C.POINTER(C.c_int)]
     H.hh_solve_branch_oracle_eval.argtypes = [C.c_void_p, C.c_void_p, pd, pd, pd, pd, pd, C.c_longlong, C.c_int,
                                               C.c_double, C.c_double, C.POINTER(C.c_int)]
     H.hh_eval.argtypes = [pd, pd, pd, C.c_double, pd, pd, pd]

@@ -3,7 +3,6 @@
 // suite can drive exactly the code the GPU runs (flattened AL/TRON loop, masked
 // free-set) against the oracle without a GPU. Not part of the product library.
 #include "../../exaadmm.jl_b200/csrc/branch.cuh"
-#include "../../exaadmm.jl_b200/csrc/chain.cuh"
 #include "../../exaadmm.jl_b200/csrc/genramp.cuh"
 #include "../../exaadmm.jl_b200/csrc/qpsub.cuh"
 #include <cmath>
@@ -62,9 +61,6 @@ static void run(const Eval &eval, double *x, const double *xl, const double *xu,
 }
 
 extern "C" {
-#ifdef EA_TRON_STATS
-void hh_stats(long long *o) { auto &d = tron::dbg(); o[0]=d.spcg; o[1]=d.simple; o[2]=d.faces2; o[3]=d.shift; o[4]=d.cgmulti; o[5]=d.tr; o[6]=d.proj; o[7]=d.nofree; }
-#endif
 
 // param: 31 doubles (membuf column, 0-based rows); rows 24-26 (lambda_s, mu) updated in place.
 // x: 6 doubles in/out. Y: 8. xl/xu: 6. work[6]: auglag, evals, cg, shifts, rejected, hit_max.
@@ -74,53 +70,6 @@ void hh_solve_branch(double *x, const double *xl, const double *xu, double *para
     for (int k = 0; k < 8; ++k) { D.lam[k] = param[k]; D.rho[k] = param[8 + k]; D.xt[k] = param[16 + k]; D.Y[k] = Y[k]; }
     const branch::Objective<branch::StructView> eval{ { &D }, scale };
     run(eval, x, xl, xu, param, major_iter, max_auglag, mu_max, F, work);
-}
-
-// The same branch through the chain driver (chain.cuh): the first `hand_al` AL iterations by the state machine, the rest
-// by chain::al_iteration - exactly what k_xupdate does with its two kinds of warps (hand_al = 0: chain driver from the
-// start). Must give the same bits as hh_solve_branch.
-void hh_solve_chain(double *x, const double *xl, const double *xu, double *param, const double *Y,
-                    long long major_iter, int max_auglag, double mu_max, double scale, int hand_al, double *F, int *work) {
-    branch::Data D;
-    for (int k = 0; k < 8; ++k) { D.lam[k] = param[k]; D.rho[k] = param[8 + k]; D.xt[k] = param[16 + k]; D.Y[k] = Y[k]; }
-    const branch::StructView V{ &D };
-    const branch::Objective<branch::StructView> eval{ V, scale };
-    branch::PowTable T;
-    make_pow_table(T, mu_max);
-    double l[6], u[6];
-    for (int k = 0; k < 6; ++k) { l[k] = xl[k]; u[k] = xu[k]; }
-    chain::State S;
-    double Fc[4] = { 0, 0, 0, 0 };
-    bool finished = false;
-    if (hand_al > 0) {
-        branch::Lane L;
-        double cold[branch::COLD_ROWS];
-        L.cold = cold; L.cs = 1;
-        for (int k = 0; k < 6; ++k) L.x[k] = x[k];
-        L.ls[0] = param[24]; L.ls[1] = param[25];
-        L.mu = (major_iter == 1) ? 10.0 : param[26];
-        branch::begin(L, T);
-        for (;;) {
-            if (branch::eval_pass(L, eval, 0, l, u, max_auglag, mu_max, T)) { finished = true; break; }
-            if (L.phase == branch::START && L.it_al >= hand_al) break;            // hand over
-            branch::eval_pass(L, eval, 1, l, u, max_auglag, mu_max, T);
-            branch::compute(L, l, u);
-        }
-        for (int k = 0; k < 6; ++k) S.x[k] = L.x[k];
-        S.ls[0] = L.ls[0]; S.ls[1] = L.ls[1]; S.mu = L.mu; S.eta = L.eta();
-        S.it_al = L.it_al; S.evals = L.evals; S.cg = L.cg; S.shifts = L.shifts; S.rejected = L.rejected; S.hit_max = L.hit_max;
-        for (int k = 0; k < 4; ++k) Fc[k] = L.Fc(k);
-    } else {
-        for (int k = 0; k < 6; ++k) S.x[k] = x[k];
-        S.ls[0] = param[24]; S.ls[1] = param[25];
-        S.mu = (major_iter == 1) ? 10.0 : param[26];
-        chain::init_state(S, T);
-    }
-    if (!finished) chain::solve(V, scale, l, u, S, Fc, max_auglag, mu_max, T);
-    for (int k = 0; k < 6; ++k) x[k] = S.x[k];
-    if (F) for (int k = 0; k < 4; ++k) F[k] = Fc[k];
-    param[24] = S.ls[0]; param[25] = S.ls[1]; param[26] = S.mu;
-    work[0] = S.it_al; work[1] = S.evals; work[2] = S.cg; work[3] = S.shifts; work[4] = S.rejected; work[5] = S.hit_max;
 }
 
 void hh_solve_branch_oracle_eval(void *fn, void *ghn, double *x, const double *xl, const double *xu, double *param,

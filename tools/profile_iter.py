@@ -26,10 +26,6 @@ assert lib.ea_init_solution(h, rho_pq, rho_va) == 0
 lib.ea_set_option(h, b"chunk", float(chunk))
 import os
 lib.ea_set_option(h, b"use_graph", float(os.environ.get("EA_USE_GRAPH", "1")))
-if "EA_HAND_AL" in os.environ:
-    lib.ea_set_option(h, b"hand_al", float(os.environ["EA_HAND_AL"]))
-if "EA_CHAIN_LANES" in os.environ:
-    lib.ea_set_option(h, b"chain_lanes", float(os.environ["EA_CHAIN_LANES"]))
 res = np.zeros(4); got = C.c_int64(); nz = C.c_double()
 lib.ea_outer_prestep(h, C.byref(nz))
 # eps_pri is never met with outer = huge -> run exactly the requested number of iterations
