@@ -77,20 +77,43 @@ EA_DEV void mu_powers(const PowTable &T, double mu, double &inv_p01, double &p09
     inv_p01 = a; p09 = b;
 }
 
-// ---- f, grad f, Hessian (packed lower) of the scaled branch AL objective, and the four flows -----------------------
-// F = (pij, qij, pji, qji) (acopf_eval_linelimit_kernel_gpu.jl:1-594, :17-22), fused, in the reduced variables
-// y = (vi, vj, t = ti - tj). All arithmetic is written with explicit fused multiply-adds: the library is compiled with
-// -fmad=false (no contraction the source does not spell out), so every instantiation of this code - the kernels, the
-// diagnostics, the host harness of the tests - rounds identically.
 #ifdef EA_PARITY
+// sin / cos for the parity build: Cody-Waite reduction by pi/2 in three parts, then the fdlibm polynomial kernels in
+// Horner form, every operation an individually rounded multiply or add. The oracle can be switched to the same
+// formulas (oracle/portable_sincos.h), which removes the last difference between its arithmetic and this build's:
+// libm's and libdevice's sin / cos disagree in the last bit for a few percent of the arguments.
+EA_DEV void psincos(double t, double *sn, double *cs) {
+    const double invpio2 = 6.36619772367581382433e-01;
+    const double pio2_1 = 1.57079632673412561417e+00, pio2_2 = 6.07710050630396597660e-11, pio2_3 = 2.02226624871116645580e-21;
+    const double pio2_3t = 8.47842766036889956997e-32;
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double fn = rint(t * invpio2);
+    double r = t - fn * pio2_1;
+    r = r - fn * pio2_2;
+    r = r - fn * pio2_3;
+    r = r - fn * pio2_3t;
+    const double z = r * r;
+    const double ps = S1 + z * (S2 + z * (S3 + z * (S4 + z * (S5 + z * S6))));
+    const double pc = C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6))));
+    const double s = r + r * (z * ps);
+    const double c = (1.0 - 0.5 * z) + z * (z * pc);
+    const long long q = (long long)fn;
+    const int k = (int)(q & 3);
+    *sn = (k == 0) ? s : ((k == 1) ? c : ((k == 2) ? -s : -c));
+    *cs = (k == 0) ? c : ((k == 1) ? -s : ((k == 2) ? -c : s));
+}
+
 // The oracle's formulas in the oracle's operation order, every operation rounded separately (oracle/acopf_oracle.c:
-// orc_eval_f, orc_eval_gh - themselves restatements of acopf_eval_linelimit_kernel_cpu.jl in compact form): with it
-// the device arithmetic of a branch solve differs from the oracle's only in sin / cos (CUDA vs glibc, <= 1-2 ulp).
+// orc_eval_f, orc_eval_gh - themselves restatements of acopf_eval_linelimit_kernel_cpu.jl in compact form).
 template <class View>
 EA_DEV void eval_fgh_ref(const View &D, const double (&ls)[2], double mu, double scale,
                          const double (&x)[N], double &f, double (&g)[N], Sym6 &A) {
     const double vi = x[0], vj = x[1], t = x[2] - x[3];
-    const double c = cos(t), s = sin(t);
+    double c, s;
+    psincos(t, &s, &c);
     const double Y0 = D.Y(0), Y1 = D.Y(1), Y2 = D.Y(2), Y3 = D.Y(3), Y4 = D.Y(4), Y5 = D.Y(5), Y6 = D.Y(6), Y7 = D.Y(7);
     const double a[4] = { Y0, -Y1, 0.0, 0.0 };
     const double b[4] = { 0.0, 0.0, Y4, -Y5 };
@@ -185,127 +208,122 @@ EA_DEV void eval_fgh_ref(const View &D, const double (&ls)[2], double mu, double
 }
 #endif
 
-// One flow F = ab v2 + vi vj P(t), P = ga cos t + de sin t: v2 = vi^2, ab = a for the from side (flows 0, 1: b = 0),
-// v2 = vj^2, ab = b for the to side (flows 2, 3: a = 0). Adds the flow's terms to the sums of its side / of the branch.
-template <bool FROM>
-EA_DEV void flow_terms(double ab, double ga, double de, double lam, double rho, double xt, double m2 /* 2 m_j */,
-                       double vi, double vj, double vv, double P, double Q, double F, double &fv, double &ABs,
-                       double &Ps, double &Qs, double (&d)[3], double (&H)[6]) {
-    const double ab2 = 2.0 * ab;
-    const double G0 = FROM ? EA_FMA(ab2, vi, vj * P) : vj * P;
-    const double G1 = FROM ? vi * P : EA_FMA(ab2, vj, vi * P);
-    const double G2 = vv * Q;
-    const double dev = F - xt;
-    fv = EA_FMA(lam, F, fv);
-    fv = EA_FMA(0.5 * (rho * dev), dev, fv);
-    const double r = EA_FMA(rho, dev, lam);
-    const double w = EA_FMA(m2, F, r);
-    const double kap = rho + m2;
-    ABs = EA_FMA(w, ab, ABs); Ps = EA_FMA(w, P, Ps); Qs = EA_FMA(w, Q, Qs);
-    const double tF = 2.0 * F;
-    d[0] = EA_FMA(tF, G0, d[0]); d[1] = EA_FMA(tF, G1, d[1]); d[2] = EA_FMA(tF, G2, d[2]);
-    const double k0 = kap * G0, k1 = kap * G1, k2 = kap * G2;
-    H[0] = EA_FMA(k0, G0, H[0]); H[1] = EA_FMA(k0, G1, H[1]); H[2] = EA_FMA(k0, G2, H[2]);
-    H[3] = EA_FMA(k1, G1, H[3]); H[4] = EA_FMA(k1, G2, H[4]); H[5] = EA_FMA(k2, G2, H[5]);
-}
-
+// Fused f, grad f, Hessian (packed lower) of the scaled branch AL objective, and the four
+// flows F = (pij, qij, pji, qji) (acopf_eval_linelimit_kernel_gpu.jl:17-22).
 template <class View>
 EA_DEV void eval_fgh(const View &D, const double (&ls)[2], double mu, double scale,
                      const double (&x)[N], double &f, double (&g)[N], Sym6 &A, double (&F)[4]) {
 #ifdef EA_PARITY
     eval_fgh_ref(D, ls, mu, scale, x, f, g, A);
     {   // flows as the AL loop of the reference computes them (acopf_auglag_linelimit_kernel_gpu.jl:98-104, 135-138)
-        const double cc = x[0] * x[1] * cos(x[2] - x[3]), ss = x[0] * x[1] * sin(x[2] - x[3]);
+        double sn, cs;
+        psincos(x[2] - x[3], &sn, &cs);
+        const double cc = x[0] * x[1] * cs, ss = x[0] * x[1] * sn;
         F[0] = D.Y(0) * (x[0] * x[0]) + D.Y(2) * cc + D.Y(3) * ss;
         F[1] = -D.Y(1) * (x[0] * x[0]) - D.Y(3) * cc + D.Y(2) * ss;
         F[2] = D.Y(4) * (x[1] * x[1]) + D.Y(6) * cc - D.Y(7) * ss;
         F[3] = -D.Y(5) * (x[1] * x[1]) - D.Y(7) * cc - D.Y(6) * ss;
     }
-#else
+    return;
+#endif
     const double vi = x[0], vj = x[1];
     double s, c;
     sincos(x[2] - x[3], &s, &c);
     const double vv = vi * vj, vi2 = vi * vi, vj2 = vj * vj;
     const double Y0 = D.Y(0), Y1 = D.Y(1), Y2 = D.Y(2), Y3 = D.Y(3), Y4 = D.Y(4), Y5 = D.Y(5), Y6 = D.Y(6), Y7 = D.Y(7);
-    // per flow: a | b, gamma, delta;  P = gamma c + delta s, Q = delta c - gamma s, F = ab v2 + vv P
-    const double ab[4] = { Y0, -Y1, Y4, -Y5 };
+    // per-flow a, b, gamma, delta
+    const double a[4] = { Y0, -Y1, 0.0, 0.0 };
+    const double b[4] = { 0.0, 0.0, Y4, -Y5 };
     const double ga[4] = { Y2, -Y3, Y6, -Y7 };
     const double de[4] = { Y3, Y2, -Y7, -Y6 };
     double P[4], Q[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        P[k] = EA_FMA(ga[k], c, de[k] * s);
-        Q[k] = EA_FMA(de[k], c, -(ga[k] * s));
-        F[k] = EA_FMA(ab[k], (k < 2) ? vi2 : vj2, vv * P[k]);
+        P[k] = ga[k] * c + de[k] * s;
+        Q[k] = de[k] * c - ga[k] * s;
+        F[k] = a[k] * vi2 + b[k] * vj2 + vv * P[k];
     }
-    const double c1 = EA_FMA(F[0], F[0], F[1] * F[1]) + x[4];
-    const double c2 = EA_FMA(F[2], F[2], F[3] * F[3]) + x[5];
-    const double m0 = EA_FMA(mu, c1, ls[0]), m1 = EA_FMA(mu, c2, ls[1]);
-    const double hm = 0.5 * mu;
-    double fv = EA_FMA(hm * c2, c2, EA_FMA(hm * c1, c1, EA_FMA(ls[1], c2, ls[0] * c1)));
-    double As = 0.0, Bs = 0.0, Ps = 0.0, Qs = 0.0;        // sum_k w_k (a, b, P, Q)_k
-    double H[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };       // reduced Hessian: 00, 01, 02, 11, 12, 22
+    const double c1 = F[0] * F[0] + F[1] * F[1] + x[4];
+    const double c2 = F[2] * F[2] + F[3] * F[3] + x[5];
+    const double m[2] = { ls[0] + mu * c1, ls[1] + mu * c2 };
+
+    double fv = ls[0] * c1 + ls[1] * c2 + 0.5 * (mu * (c1 * c1)) + 0.5 * (mu * (c2 * c2));
+    // reduced (vi, vj, t) gradient / Hessian
+    double As = 0.0, Bs = 0.0, Ps = 0.0, Qs = 0.0;        // sum_k w_k * (a,b,P,Q)_k
+    double H00 = 0.0, H01 = 0.0, H02 = 0.0, H11 = 0.0, H12 = 0.0, H22 = 0.0;
     double d[2][3] = { { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 } };
-    const double m20 = 2.0 * m0, m21 = 2.0 * m1;
-    flow_terms<true>(ab[0], ga[0], de[0], D.lam(0), D.rho(0), D.xt(0), m20, vi, vj, vv, P[0], Q[0], F[0], fv, As, Ps, Qs, d[0], H);
-    flow_terms<true>(ab[1], ga[1], de[1], D.lam(1), D.rho(1), D.xt(1), m20, vi, vj, vv, P[1], Q[1], F[1], fv, As, Ps, Qs, d[0], H);
-    flow_terms<false>(ab[2], ga[2], de[2], D.lam(2), D.rho(2), D.xt(2), m21, vi, vj, vv, P[2], Q[2], F[2], fv, Bs, Ps, Qs, d[1], H);
-    flow_terms<false>(ab[3], ga[3], de[3], D.lam(3), D.rho(3), D.xt(3), m21, vi, vj, vv, P[3], Q[3], F[3], fv, Bs, Ps, Qs, d[1], H);
-    H[0] = EA_FMA(2.0, As, H[0]); H[3] = EA_FMA(2.0, Bs, H[3]); H[1] += Ps;
-    H[2] = EA_FMA(vj, Qs, H[2]);  H[4] = EA_FMA(vi, Qs, H[4]);  H[5] = EA_FMA(-vv, Ps, H[5]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int j = k >> 1;
+        const double lam = D.lam(k), rho = D.rho(k);
+        const double dev = F[k] - D.xt(k);
+        fv += lam * F[k] + 0.5 * (rho * (dev * dev));
+        const double G0 = 2.0 * a[k] * vi + vj * P[k];
+        const double G1 = 2.0 * b[k] * vj + vi * P[k];
+        const double G2 = vv * Q[k];
+        const double r = lam + rho * dev;
+        const double w = r + 2.0 * m[j] * F[k];
+        const double kap = rho + 2.0 * m[j];
+        As += w * a[k]; Bs += w * b[k]; Ps += w * P[k]; Qs += w * Q[k];
+        const double tF = 2.0 * F[k];
+        d[j][0] += tF * G0; d[j][1] += tF * G1; d[j][2] += tF * G2;
+        const double k0 = kap * G0, k1 = kap * G1, k2 = kap * G2;
+        H00 += k0 * G0; H01 += k0 * G1; H02 += k0 * G2;
+        H11 += k1 * G1; H12 += k1 * G2; H22 += k2 * G2;
+    }
+    H00 += 2.0 * As; H11 += 2.0 * Bs; H01 += Ps;
+    H02 += vj * Qs;  H12 += vi * Qs;  H22 -= vv * Ps;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        const double a0 = mu * d[j][0], a1 = mu * d[j][1], a2 = mu * d[j][2];
-        H[0] = EA_FMA(a0, d[j][0], H[0]); H[1] = EA_FMA(a0, d[j][1], H[1]); H[2] = EA_FMA(a0, d[j][2], H[2]);
-        H[3] = EA_FMA(a1, d[j][1], H[3]); H[4] = EA_FMA(a1, d[j][2], H[4]); H[5] = EA_FMA(a2, d[j][2], H[5]);
+        const double m0 = mu * d[j][0], m1 = mu * d[j][1], m2 = mu * d[j][2];
+        H00 += m0 * d[j][0]; H01 += m0 * d[j][1]; H02 += m0 * d[j][2];
+        H11 += m1 * d[j][1]; H12 += m1 * d[j][2]; H22 += m2 * d[j][2];
     }
     // consensus terms on w_i = vi^2, w_j = vj^2, t_i, t_j
     const double rho4 = D.rho(4), rho5 = D.rho(5), rho6 = D.rho(6), rho7 = D.rho(7);
-    const double lam4 = D.lam(4), lam5 = D.lam(5), lam6 = D.lam(6), lam7 = D.lam(7);
     const double dwi = vi2 - D.xt(4), dwj = vj2 - D.xt(5), dti = x[2] - D.xt(6), dtj = x[3] - D.xt(7);
-    fv = EA_FMA(lam4, vi2, fv); fv = EA_FMA(0.5 * (rho4 * dwi), dwi, fv);
-    fv = EA_FMA(lam5, vj2, fv); fv = EA_FMA(0.5 * (rho5 * dwj), dwj, fv);
-    fv = EA_FMA(lam6, x[2], fv); fv = EA_FMA(0.5 * (rho6 * dti), dti, fv);
-    fv = EA_FMA(lam7, x[3], fv); fv = EA_FMA(0.5 * (rho7 * dtj), dtj, fv);
+    const double lam4 = D.lam(4), lam5 = D.lam(5), lam6 = D.lam(6), lam7 = D.lam(7);
+    fv += lam4 * vi2 + 0.5 * (rho4 * (dwi * dwi)) + lam5 * vj2 + 0.5 * (rho5 * (dwj * dwj))
+        + lam6 * x[2] + 0.5 * (rho6 * (dti * dti)) + lam7 * x[3] + 0.5 * (rho7 * (dtj * dtj));
     f = scale * fv;
-    const double ri = EA_FMA(rho4, dwi, lam4), rj = EA_FMA(rho5, dwj, lam5);
-    const double gy0 = EA_FMA(2.0 * vi, ri, EA_FMA(vj, Ps, (2.0 * As) * vi));
-    const double gy1 = EA_FMA(2.0 * vj, rj, EA_FMA(vi, Ps, (2.0 * Bs) * vj));
+    const double ri = lam4 + rho4 * dwi;
+    const double rj = lam5 + rho5 * dwj;
+    const double gy0 = 2.0 * As * vi + vj * Ps + 2.0 * vi * ri;
+    const double gy1 = 2.0 * Bs * vj + vi * Ps + 2.0 * vj * rj;
     const double gy2 = vv * Qs;
-    H[0] = EA_FMA(4.0 * rho4, vi2, EA_FMA(2.0, ri, H[0]));
-    H[3] = EA_FMA(4.0 * rho5, vj2, EA_FMA(2.0, rj, H[3]));
+    H00 += 2.0 * ri + 4.0 * rho4 * vi2;
+    H11 += 2.0 * rj + 4.0 * rho5 * vj2;
+
     g[0] = scale * gy0;
     g[1] = scale * gy1;
-    g[2] = scale * (gy2 + EA_FMA(rho6, dti, lam6));
-    g[3] = scale * (EA_FMA(rho7, dtj, lam7) - gy2);
-    g[4] = scale * m0;
-    g[5] = scale * m1;
+    g[2] = scale * (gy2 + lam6 + rho6 * dti);
+    g[3] = scale * (-gy2 + lam7 + rho7 * dtj);
+    g[4] = scale * m[0];
+    g[5] = scale * m[1];
+
     using tron::tri;
     const double smu = scale * mu;
-    const double h02 = scale * H[2], h12 = scale * H[4], h22 = scale * H[5];
-    A.a[tri(0, 0)] = scale * H[0];
-    A.a[tri(1, 0)] = scale * H[1];
-    A.a[tri(1, 1)] = scale * H[3];
-    A.a[tri(2, 0)] = h02;
-    A.a[tri(2, 1)] = h12;
-    A.a[tri(2, 2)] = scale * (H[5] + rho6);
-    A.a[tri(3, 0)] = -h02;
-    A.a[tri(3, 1)] = -h12;
-    A.a[tri(3, 2)] = -h22;
-    A.a[tri(3, 3)] = scale * (H[5] + rho7);
-    const double s02 = smu * d[0][2], s12 = smu * d[1][2];
+    A.a[tri(0, 0)] = scale * H00;
+    A.a[tri(1, 0)] = scale * H01;
+    A.a[tri(1, 1)] = scale * H11;
+    A.a[tri(2, 0)] = scale * H02;
+    A.a[tri(2, 1)] = scale * H12;
+    A.a[tri(2, 2)] = scale * (H22 + rho6);
+    A.a[tri(3, 0)] = -(scale * H02);
+    A.a[tri(3, 1)] = -(scale * H12);
+    A.a[tri(3, 2)] = -(scale * H22);
+    A.a[tri(3, 3)] = scale * (H22 + rho7);
     A.a[tri(4, 0)] = smu * d[0][0];
     A.a[tri(4, 1)] = smu * d[0][1];
-    A.a[tri(4, 2)] = s02;
-    A.a[tri(4, 3)] = -s02;
+    A.a[tri(4, 2)] = smu * d[0][2];
+    A.a[tri(4, 3)] = -(smu * d[0][2]);
     A.a[tri(4, 4)] = smu;
     A.a[tri(5, 0)] = smu * d[1][0];
     A.a[tri(5, 1)] = smu * d[1][1];
-    A.a[tri(5, 2)] = s12;
-    A.a[tri(5, 3)] = -s12;
+    A.a[tri(5, 2)] = smu * d[1][2];
+    A.a[tri(5, 3)] = -(smu * d[1][2]);
     A.a[tri(5, 4)] = 0.0;
     A.a[tri(5, 5)] = smu;
-#endif
 }
 
 // The branch objective bound to a data view (what the kernel and the harness plug into Lane).
@@ -457,16 +475,7 @@ EA_DEV void compute(Lane &L, const double (&xl)[N], const double (&xu)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) L.xc(i) = L.x[i];
     tron::Stats st;
-    // A branch past its first AL iteration is on the penalty ladder: its solves are Newton steps from a warm start, so the
-    // direct Newton step of tron.cuh is tried first (93 % success). First iterations take the literal algorithm alone:
-    // they run in full warps, where a failed attempt of one lane costs every lane the time of both paths. The rule
-    // depends on the branch's own history only, so a branch gives the same bits wherever and whenever it is solved.
-#ifndef EA_NEWTON_MODE
-#define EA_NEWTON_MODE 1
-#endif
-    const bool try_newton = (EA_NEWTON_MODE == 2) || (EA_NEWTON_MODE == 1 && L.it_al >= 1);
-    if (!(try_newton && tron::newton_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st)))
-        tron::compute_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st);
+    tron::compute_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st);
     L.cg += st.cg;
     L.shifts += st.shifts;
     L.phase = TRIAL;

@@ -104,6 +104,16 @@ __device__ __forceinline__ void st4(double *base, int slot, const d4 &v) {
     *reinterpret_cast<double2 *>(base + 4 * (size_t)slot + 2) = make_double2(v.w, v.t);
 }
 
+// a / b where 1 / b is at hand: the fast build multiplies by the reciprocal; EA_EXACT (parity build) divides, as the
+// reference does, so that the bus update rounds like the CPU path's (acopf_bus_kernel_cpu.jl)
+__device__ __forceinline__ double quot(double a, double b, double ib) {
+#if EA_EXACT
+    (void)ib; return a / b;
+#else
+    (void)b; return a * ib;
+#endif
+}
+
 // z, lambda updates (acopf_admm_update_z_gpu.jl:1-11, acopf_admm_update_l_gpu.jl:1-14)
 __device__ __forceinline__ double z_update(double lz, double l, double rho, double u, double v, double beta) {
     return tron::ddiv(-(lz + l + rho * (u - v)), beta + rho);      // Newton-refined reciprocal: no slow-path branch
@@ -413,7 +423,7 @@ __device__ __forceinline__ void bus_gen_gather(const Dev &d, const double *zold,
     const double2 l = *reinterpret_cast<const double2 *>(d.l + 2 * k);
     const double2 r = *reinterpret_cast<const double2 *>(d.rho + 2 * k);
     const double iy = tron::ddiv(1.0, r.y);
-    rhs2 += (u.y + z.y) + (l.y * iy);
+    rhs2 += (u.y + z.y) + quot(l.y, r.y, iy);
     inv_qg += iy;
     if (d.rn_u) {                          // ramp-coupled generator (mpacopf_bus_kernel_gpu.jl:47-60)
         const double rr = d.rn_rho[k];
@@ -422,7 +432,7 @@ __device__ __forceinline__ void bus_gen_gather(const Dev &d, const double *zold,
         inv_pg += ix;
     } else {
         const double ix = tron::ddiv(1.0, r.x);
-        rhs1 += (u.x + z.x) + (l.x * ix);
+        rhs1 += (u.x + z.x) + quot(l.x, r.x, ix);
         inv_pg += ix;
     }
 }
@@ -432,19 +442,19 @@ __device__ __forceinline__ BusSolve bus_solve(const Dev &d, int b, double common
                                               double inv_q, double rs_w, double rs_t, double rhs1, double rhs2,
                                               double inv_pg, double inv_qg) {
     const double irw = tron::ddiv(1.0, rs_w);
-    common_wi *= irw;
+    common_wi = quot(common_wi, rs_w, irw);
     const double gr = d.YshR[b], gi = d.YshI[b];
     rhs1 -= gr * common_wi;
     rhs2 += gi * common_wi;
-    const double A11 = (inv_pg + inv_p) + (gr * gr * irw);
-    const double A12 = -gr * (gi * irw);
+    const double A11 = (inv_pg + inv_p) + quot(gr * gr, rs_w, irw);
+    const double A12 = -gr * quot(gi, rs_w, irw);
     const double A21 = A12;
-    const double A22 = (inv_qg + inv_q) + (gi * gi * irw);
+    const double A22 = (inv_qg + inv_q) + quot(gi * gi, rs_w, irw);
     const double iA11 = tron::ddiv(1.0, A11);
     BusSolve s;
-    s.mu2 = tron::ddiv(rhs2 - (A21 * iA11) * rhs1, A22 - (A21 * iA11) * A12);
-    s.mu1 = (rhs1 - A12 * s.mu2) * iA11;
-    s.wi = common_wi + ((gr * s.mu1 - gi * s.mu2) * irw);
+    s.mu2 = tron::ddiv(rhs2 - quot(A21, A11, iA11) * rhs1, A22 - quot(A21, A11, iA11) * A12);
+    s.mu1 = quot(rhs1 - A12 * s.mu2, A11, iA11);
+    s.wi = common_wi + quot(gr * s.mu1 - gi * s.mu2, rs_w, irw);
     s.ti = tron::ddiv(common_ti, rs_t);
     return s;
 }
@@ -461,8 +471,8 @@ __device__ __forceinline__ void bus_gen_scatter(const Dev &d, const double *zold
         const double rr = d.rn_rho[k];
         v.x = ((l.x + r.x * (u.x + z.x)) + (d.rn_l[k] + rr * (d.rn_u[k] + d.rn_z[zsel][k])) - bs.mu1) * tron::ddiv(1.0, r.x + rr);
     } else
-        v.x = (u.x + z.x) + (l.x - bs.mu1) * tron::ddiv(1.0, r.x);
-    v.y = (u.y + z.y) + (l.y - bs.mu2) * tron::ddiv(1.0, r.y);
+        v.x = (u.x + z.x) + quot(l.x - bs.mu1, r.x, tron::ddiv(1.0, r.x));
+    v.y = (u.y + z.y) + quot(l.y - bs.mu2, r.y, tron::ddiv(1.0, r.y));
     *reinterpret_cast<double2 *>(d.v + 2 * k) = v;
     if (FUSED) {
         const double2 lz = *reinterpret_cast<const double2 *>(d.lz + 2 * k);
@@ -489,8 +499,8 @@ __device__ __forceinline__ void bus_end_scatter(const Dev &d, double *znew, int 
                                                 const d4 &r, double irp, double irq, const BusSolve &bs, double beta,
                                                 double (&acc)[4]) {
     d4 v;
-    v.p = (u.p + z.p) + (l.p + bs.mu1) * irp;
-    v.q = (u.q + z.q) + (l.q + bs.mu2) * irq;
+    v.p = (u.p + z.p) + quot(l.p + bs.mu1, r.p, irp);
+    v.q = (u.q + z.q) + quot(l.q + bs.mu2, r.q, irq);
     v.w = bs.wi;
     v.t = bs.ti;
     st4(d.v + d.gpad, s, v);
@@ -543,8 +553,8 @@ __device__ __forceinline__ void bus_scalar(const Dev &d, const double *zold, dou
         inv_q += irq;
         rs_w += r.w;
         rs_t += r.t;
-        rhs1 -= (u.p + z.p) + (l.p * irp);
-        rhs2 -= (u.q + z.q) + (l.q * irq);
+        rhs1 -= (u.p + z.p) + quot(l.p, r.p, irp);
+        rhs2 -= (u.q + z.q) + quot(l.q, r.q, irq);
     }
     const BusSolve bs = bus_solve(d, b, common_wi, common_ti, inv_p, inv_q, rs_w, rs_t, rhs1, rhs2, inv_pg, inv_qg);
     for (int k = gs; k < ge; ++k) bus_gen_scatter<FUSED>(d, zold, znew, zsel, k, bs, beta, acc);
@@ -582,8 +592,8 @@ __device__ __forceinline__ void bus_body(const Dev &d, int zsel_arg, double beta
             const double t_w = l.w + r.w * (u.w + z.w);
             const double t_t = l.t + r.t * (u.t + z.t);
             const double t_ip = tron::ddiv(1.0, r.p), t_iq = tron::ddiv(1.0, r.q);
-            const double t_p = (u.p + z.p) + (l.p * t_ip);
-            const double t_q = (u.q + z.q) + (l.q * t_iq);
+            const double t_p = (u.p + z.p) + quot(l.p, r.p, t_ip);
+            const double t_q = (u.q + z.q) + quot(l.q, r.q, t_iq);
             double common_wi = 0.0, common_ti = 0.0, inv_p = 0.0, inv_q = 0.0, rs_w = 0.0, rs_t = 0.0;
             double rhs1 = 0.0, rhs2 = 0.0, inv_pg = 0.0, inv_qg = 0.0;
             int gs = 0, ge = 0;

@@ -60,9 +60,18 @@ static double dmax(double a, double b) { return a > b ? a : b; }
 /* ------------------------------------------------------------------------ */
 typedef struct { double a, b, P, Q, F; } flow_t;
 
+#include "portable_sincos.h"
+static int g_portable_sincos = 0;
+void orc_set_portable_sincos(int on) { g_portable_sincos = on; }
+static void orc_sincos(double t, double *s, double *c) {
+    if (g_portable_sincos) psincos(t, s, c);
+    else { *s = sin(t); *c = cos(t); }
+}
+
 static void flow_terms(const double x[6], const double Y[8], flow_t fl[4]) {
     const double vi = x[0], vj = x[1], t = x[2] - x[3];
-    const double c = cos(t), s = sin(t);
+    double c, s;
+    orc_sincos(t, &s, &c);
     /* rows: pij, qij, pji, qji (eval_cpu.jl:13-16) */
     const double a[4] = { Y[0], -Y[1], 0.0, 0.0 };
     const double b[4] = { 0.0, 0.0, Y[4], -Y[5] };
@@ -680,8 +689,10 @@ static void solve_branch(orc_model_t *m, int64_t I, int64_t major_iter, int32_t 
         it++;
         int minor;
         tron_solve(x, xl, xu, param, Y, scale, 500, 200, 1e-6, &minor, &st);
-        const double cc = x[0] * x[1] * cos(x[2] - x[3]);
-        const double ss = x[0] * x[1] * sin(x[2] - x[3]);
+        double sn, cs;
+        orc_sincos(x[2] - x[3], &sn, &cs);
+        const double cc = x[0] * x[1] * cs;
+        const double ss = x[0] * x[1] * sn;
         const double fpij = Y[0] * (x[0] * x[0]) + Y[2] * cc + Y[3] * ss;
         const double fqij = -Y[1] * (x[0] * x[0]) - Y[3] * cc + Y[2] * ss;
         const double fpji = Y[4] * (x[1] * x[1]) + Y[6] * cc - Y[7] * ss;
@@ -703,8 +714,10 @@ static void solve_branch(orc_model_t *m, int64_t I, int64_t major_iter, int32_t 
         }
         if (it >= max_auglag) { if (!terminate) cnt->max_auglag_hits++; terminate = 1; }
     }
-    const double cc = x[0] * x[1] * cos(x[2] - x[3]);
-    const double ss = x[0] * x[1] * sin(x[2] - x[3]);
+    double sn, cs;
+    orc_sincos(x[2] - x[3], &sn, &cs);
+    const double cc = x[0] * x[1] * cs;
+    const double ss = x[0] * x[1] * sn;
     u[pij] = Y[0] * (x[0] * x[0]) + Y[2] * cc + Y[3] * ss;
     u[pij + 1] = -Y[1] * (x[0] * x[0]) - Y[3] * cc + Y[2] * ss;
     u[pij + 2] = Y[4] * (x[1] * x[1]) + Y[6] * cc - Y[7] * ss;

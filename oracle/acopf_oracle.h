@@ -29,6 +29,8 @@ typedef struct orc_model orc_model_t;
 int    orc_create(const ea_grid_t *grid, orc_model_t **out);
 void   orc_destroy(orc_model_t *m);
 void   orc_set_threads(orc_model_t *m, int nthreads);   /* 1 = faithful serial loops */
+/* 1: the branch objective uses the portable sin / cos of portable_sincos.h (process-wide), 0: libm (default) */
+void   orc_set_portable_sincos(int on);
 int    orc_get_threads(const orc_model_t *m);
 
 void   orc_init_solution(orc_model_t *m, double rho_pq, double rho_va);

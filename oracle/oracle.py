@@ -46,6 +46,8 @@ def lib():
         L.orc_create.restype = C.c_int
         L.orc_destroy.argtypes = [H]
         L.orc_set_threads.argtypes = [H, C.c_int]
+        L.orc_set_portable_sincos.argtypes = [C.c_int]
+        L.orc_set_portable_sincos.restype = None
         L.orc_get_threads.argtypes = [H]
         L.orc_get_threads.restype = C.c_int
         L.orc_init_solution.argtypes = [H, C.c_double, C.c_double]
@@ -138,6 +140,12 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(_pd)
+
+
+def set_portable_sincos(on: bool) -> None:
+    """Process-wide: the oracle's branch objective uses the portable sin / cos shared with the PARITY build of the CUDA
+    library (oracle/portable_sincos.h) instead of libm. For bit-for-bit comparisons with that build only."""
+    lib().orc_set_portable_sincos(1 if on else 0)
 
 
 class OracleModel:

@@ -82,6 +82,13 @@ def host_harness_nofma():
     return _load_harness("_build_host_harness_nofma.so")
 
 
+@pytest.fixture(scope="session")
+def host_harness_parity():
+    """Same, with the arithmetic of the library's PARITY build (-DEA_NO_FMA -DEA_PARITY): the product's own
+    objective in the oracle's operation order."""
+    return _load_harness("_build_host_harness_parity.so")
+
+
 def branch_inputs(grid, u, v, z, l, rho, membuf, I):
     """Inputs of one branch sub-problem as the reference stages them
     (acopf_auglag_linelimit_kernel_cpu.jl:23-80)."""
@@ -92,7 +99,7 @@ def branch_inputs(grid, u, v, z, l, rho, membuf, I):
     xu = np.array([grid.FrVmBound[2 * I + 1], grid.ToVmBound[2 * I + 1], grid.FrVaBound[2 * I + 1],
                    grid.ToVaBound[2 * I + 1], 0.0, 0.0])
     x = np.array([math.sqrt(u[p + 4]), math.sqrt(u[p + 5]), u[p + 6], u[p + 7],
-                  -(u[p] ** 2 + u[p + 1] ** 2), -(u[p + 2] ** 2 + u[p + 3] ** 2)])
+                  -(u[p] * u[p] + u[p + 1] * u[p + 1]), -(u[p + 2] * u[p + 2] + u[p + 3] * u[p + 3])])   # not ** 2: pow() may round differently
     x = np.minimum(xu, np.maximum(xl, x))
     param = np.zeros(31)
     param[0:8] = l[p:p + 8]

@@ -56,7 +56,7 @@ def _run_lockstep(host_harness, grid, par, rho_pq, rho_va, n_iter, tol):
             host_harness.hh_solve_branch(P(x), P(xl), P(xu), P(param), P(Y), m.inner, par.max_auglag, par.mu_max,
                                          par.scale, P(F), work)
             p = 2 * ng + 8 * I
-            uo = np.array([F[0], F[1], F[2], F[3], x[0] ** 2, x[1] ** 2, x[2], x[3]])
+            uo = np.array([F[0], F[1], F[2], F[3], x[0] * x[0], x[1] * x[1], x[2], x[3]])
             worst = max(worst, np.abs(uo - u2[p:p + 8]).max())
             assert param[26] == mb2[26, I]                                     # mu: exact (powers of ten)
             worst = max(worst, np.abs(param[24:26] - mb2[24:26, I]).max() / max(1.0, param[26]))
@@ -113,6 +113,26 @@ def test_tron_logic_is_bit_identical_to_oracle_on_hard_problems(host_harness_nof
         np.testing.assert_array_equal(xc, xo)
         shifts += work[3]; rejected += work[4]
     assert shifts > 100 and rejected > 1000               # the hard paths were really exercised
+
+
+def test_parity_build_arithmetic_is_bit_identical_to_oracle(host_harness_parity):
+    """The library's PARITY build (csrc/Makefile: -fmad=false -DEA_NO_FMA -DEA_PARITY), compiled for the host: the
+    product's own objective (branch::eval_fgh_ref, portable sin / cos) inside the product's AL / TRON state machine
+    against the oracle switched to the same sin / cos - every branch of every iteration must give the same BITS
+    (u, lambda_s, mu) and the same evaluation count. On the GPU the same source differs only in where it runs
+    (tests/test_gpu_baseline_configs.py compares that build with the oracle over whole iterations)."""
+    from oracle.oracle import set_portable_sincos
+    set_portable_sincos(True)
+    try:
+        par = Parameters(); par.verbose = 0
+        d = synthetic_case(60, 12, 84, seed=60, rate_margin=1.02)         # limits bind: the penalty ladder is exercised
+        grid = ea.GridData.from_opfdata(d, tight_factor=0.99)
+        _run_lockstep(host_harness_parity, grid, par, 4e2, 4e4, 25, 0.0)
+        d = synthetic_case(300, 40, 420, seed=300)
+        grid = ea.GridData.from_opfdata(d, tight_factor=0.99)
+        _run_lockstep(host_harness_parity, grid, par, 1e1, 1e3, 12, 0.0)   # README rho of the pegase cases: rejected steps
+    finally:
+        set_portable_sincos(False)
 
 
 def test_branch_solver_random_problems_fma_build(host_harness):

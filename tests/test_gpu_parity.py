@@ -492,3 +492,34 @@ def test_full_size_properties_activsg70k_like():
     assert mod.info.primres == pytest.approx(np.linalg.norm(u - v + z), rel=1e-12)
     assert mod.info.mismatch == pytest.approx(np.linalg.norm(u - v), rel=1e-10)
     mod.close()
+
+
+def test_hardest_branches_of_a_real_solve_device_vs_host_build():
+    """tests/golden/hard_branches.npz (tools/make_hard_branches.py): the branches of ACTIVSg70k-like inner iterations that
+    need the most objective evaluations - penalty ladders of 20-25 AL iterations, trust-region-limited solves at
+    mu = 1e8 with rejected steps and Cholesky shifts - plus a sample of ordinary ones, with the solutions of the HOST
+    build of the device code. The kernel's branch driver must reproduce them (same AL iterations, same evaluation
+    counts but for the few solves whose path is rounding-sensitive) and must not depend on how lanes share a warp."""
+    import ctypes as C
+    from pathlib import Path
+    from exaadmm_b200 import capi
+    d = np.load(Path(__file__).resolve().parent / "golden" / "hard_branches.npz")
+    prob, sol0, work0, meta = np.ascontiguousarray(d["prob"]), d["sol"], d["work"], d["meta"]
+    lib = capi.load_library()
+    n = prob.shape[0]
+    out = {}
+    for per_warp in (0, 1):
+        sol = np.zeros((n, 13)); work = np.zeros((n, 6), dtype=np.int32); cyc = np.zeros(n, dtype=np.int64); ms = C.c_double()
+        rc = lib.ea_diag_branch_solve(0, per_warp, n, capi.dptr(prob), int(meta[2]), float(meta[1]), float(meta[0]),
+                                      capi.dptr(sol), work.ctypes.data_as(C.POINTER(C.c_int32)),
+                                      cyc.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(ms))
+        assert rc == 0, lib.ea_last_error(None)
+        out[per_warp] = (sol, work)
+    np.testing.assert_array_equal(out[0][0], out[1][0])              # one problem per lane == one per warp, bit for bit
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    sol, work = out[0]
+    assert work0[:, 1].max() >= 150 and (work0[:, 0] >= 20).sum() >= 50      # the fixture really holds the hard ones
+    np.testing.assert_array_equal(work[:, 0], work0[:, 0])                    # AL iterations
+    assert np.mean(work[:, 1] == work0[:, 1]) >= 0.97                         # evaluations (libdevice vs libm sincos)
+    same = work[:, 1] == work0[:, 1]
+    np.testing.assert_allclose(sol[same, :10], sol0[same, :10], rtol=0, atol=1e-6)
