@@ -23,8 +23,14 @@ state is re-initialised and the trajectory restarts).
   cpu_baseline   the CPU oracle (restatement of the reference's use_gpu=false path)
                  on 1 host core, bounded sample
 
-Multi-GPU (N>1, torchrun): independent load scenarios sharded over ranks, one
-process per GPU, no data-path collective ("scaling": "weak").
+Multi-GPU (N>1, torchrun, one process per GPU): the SAME solve, bus-partitioned over the N GPUs
+(BASELINE configs 3-4; exaadmm.jl_b200/partition.py: graph cut, cut branches solved redundantly, one exchange
+per inner iteration - xbar halves of the cut-branch ends + residual partial sums - by peer-memory stores over
+NVLink fused into the bus kernel, or ncclAllGather with --exchange nccl). "scaling": "strong": value = inner
+iterations of the one solve per second. Rank 0 also solves the case on one GPU and the run FAILS unless the
+partitioned solve ends with the same status / outer / cumulative count and objective (`partition_parity`).
+--mode replicas keeps the round-1 weak-scaling measurement (independent load scenarios, no collective);
+its number is also reported as the secondary key `replicas`.
 """
 from __future__ import annotations
 
@@ -178,6 +184,16 @@ def run_reference(args, rank, world):
         m.inner_iteration()
     dt = time.perf_counter() - t0
     val = args.steps / dt
+    # the reference's CPU path is serial (acopf_auglag_linelimit_kernel_cpu.jl:21 `for I=...`, acopf_bus_kernel_cpu.jl:11):
+    # the faithful figure is ONE thread; measured on a short sample of the same iterations
+    m1 = OracleModel(grid, par, rho_pq, rho_va)
+    m1.set_threads(1)
+    m1.admm_increment_outer(); m1.admm_outer_prestep(); m1.admm_increment_reset_inner()
+    n1 = max(3, min(args.steps, 10))
+    t1 = time.perf_counter()
+    for _ in range(n1):
+        m1.inner_iteration()
+    val1 = n1 / (time.perf_counter() - t1)
     line = {
         "impl": "reference", "metric": "admm_inner_iterations_per_sec", "value": val, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -185,8 +201,11 @@ def run_reference(args, rank, world):
         "config": dict(base_config(args.workload, grid, par, rho_pq, rho_va),
                        parallelism=f"{threads} host threads (OpenMP over branches and buses), rank 0 only"),
         "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": threads, "kind": "port",
-                         "sample": f"first {args.warmup}+{args.steps} inner iterations of the solve, full grid, "
-                                   f"OpenMP over branches and buses (oracle restatement, not Julia)"},
+                         "sample": f"first {args.warmup}+{args.steps} inner iterations of the solve, full grid; C restatement "
+                                   f"of the reference's CPU path with OpenMP over branches and buses on {threads} threads - "
+                                   f"NOT reference behaviour (the reference's CPU loops are serial, and it is Julia)",
+                         "value_1_thread": val1,
+                         "sample_1_thread": f"first {n1} inner iterations, serial loops as in the reference"},
         "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -207,53 +226,126 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    grid, _ = make_grid(args.workload)
+    grid, data = make_grid(args.workload)
     par, rho_pq, rho_va = default_params(args.workload)
-    if world > 1:
-        # scenario sharding: rank r solves load scenario r: every (Pd, Qd) scaled by iid U[0.99, 1.01], seed nbus + r.
-        # (+-5 % per bus, the spread SURVEY 8d suggests, makes this synthetic grid stall - 20 x 1000 iterations without
-        #  converging, oracle and GPU alike - while +-1 % converges like the base case: 12 outer / 447 inner iterations.)
-        rng = np.random.default_rng(grid.nbus + rank)
-        f = rng.uniform(0.99, 1.01, grid.nbus)
-        grid.Pd = grid.Pd * f
-        grid.Qd = grid.Qd * f
-    nvar = 2 * grid.ngen + 8 * grid.nline
-    gs, keep = make_grid_struct(grid)
+    partitioned = world > 1 and args.mode == "partitioned"
+    nvar = 2 * grid.ngen + 8 * grid.nline                    # of the whole problem (tolerances scale with sqrt(nvar))
 
     def check(rc, h=None):
         if rc != 0:
             raise RuntimeError(f"exaadmm_b200 error {rc}: {(lib.ea_last_error(h) or b'').decode()}")
 
+    def scenario_grid(r):
+        # scenario sharding (--mode replicas): rank r solves load scenario r: every (Pd, Qd) scaled by iid U[0.99, 1.01],
+        # seed nbus + r. (+-5 % per bus, the spread SURVEY 8d suggests, makes this synthetic grid stall - 20 x 1000
+        # iterations without converging, oracle and GPU alike - while +-1 % converges like the base case.)
+        import copy
+        g = copy.copy(grid)
+        f = np.random.default_rng(grid.nbus + r).uniform(0.99, 1.01, grid.nbus)
+        g.Pd = grid.Pd * f
+        g.Qd = grid.Qd * f
+        return g
+
+    # ---- what one rank holds: the whole grid (1 GPU / replicas) or its part of the bus partition ----------------------
+    part_info = None
+    if partitioned:
+        from exaadmm_b200.environment import AdmmEnv
+        from exaadmm_b200.partition import partition_buses, cut_statistics
+        from exaadmm_b200.partitioned import make_partitioned_model, init_comm, init_peer_exchange
+        part = partition_buses(grid, world)
+        env = AdmmEnv(data, rho_pq, rho_va, use_gpu=True, tight_factor=0.99, gpu_no=local_rank, verbose=0)
+
+        def new_handle():
+            t0 = time.perf_counter()
+            mod, lg = make_partitioned_model(env, grid, part, rank)        # ea_create(rank-local grid) + ea_set_partition
+            t1 = time.perf_counter()
+            init_comm(mod, rank)                                          # NCCL communicator of the handle (scalar collectives)
+            if args.exchange == "peer":
+                init_peer_exchange(mod)                                   # CUDA IPC: peer stores replace the all-gather
+            part_info["message_bytes_per_rank_per_iteration"] = 8 * (4 + 4 * lg.max_send)
+            return mod, mod.h, lg.grid, t1 - t0
+        stats = cut_statistics(grid, part)
+        part_info = {"parts": world, "cut": stats, "exchange": args.exchange}
+    else:
+        my_grid = scenario_grid(rank) if world > 1 else grid
+        gs, keep = make_grid_struct(my_grid)
+
+        def new_handle():
+            t0 = time.perf_counter()
+            h = C.c_void_p()
+            check(lib.ea_create(C.byref(gs), local_rank, C.byref(h)))
+            return None, h, my_grid, time.perf_counter() - t0
+
+    def drop_handle(mod, h):
+        if mod is not None:
+            mod.close()
+        else:
+            lib.ea_destroy(h)
+
     # ---------------- e2e: the call a user makes (host arrays in, solution on host out) -------------
     def solve_e2e():
-        u = np.empty(nvar)
         p = params_struct(par)
         info = EaInfo()
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
-        h = C.c_void_p()
-        check(lib.ea_create(C.byref(gs), local_rank, C.byref(h)))
+        mod, h, lgrid, t_create = new_handle()
         t1 = time.perf_counter()
         check(lib.ea_init_solution(h, rho_pq, rho_va), h)
         check(lib.ea_set_option(h, b"count_work", 0.0), h)
         check(lib.ea_admm_two_level(h, C.byref(p), C.byref(info)), h)
         t2 = time.perf_counter()
-        check(lib.ea_get_vector(h, 0, dptr(u), nvar), h)
-        dt = time.perf_counter() - t0
-        lib.ea_destroy(h)
-        return info, dt, {"create_h2d_s": t1 - t0, "init_and_solve_s": t2 - t1, "d2h_s": dt - (t2 - t0)}
+        n_local = 2 * lgrid.ngen + 8 * lgrid.nline
+        u = np.empty(n_local)
+        check(lib.ea_get_vector(h, 0, dptr(u), n_local), h)
+        t3 = time.perf_counter()
+        drop_handle(mod, h)
+        # partitioned: the communicator / IPC set-up of the handle (one-off per process group in a deployment) is timed
+        # separately and not part of the end-to-end figure; ea_create + H2D of the local grid is
+        dt = t_create + (t3 - t1)
+        return info, dt, {"create_h2d_s": t_create, "comm_setup_s": (t1 - t0) - t_create, "init_and_solve_s": t2 - t1,
+                          "d2h_s": t3 - t2}, lgrid
 
     solve_e2e()                                   # warm-up (context, module load)
-    solve_e2e()
-    info_e2e, t_e2e, e2e_split = solve_e2e()
-    grid_bytes = sum(getattr(grid, n).nbytes for n in capi._GRID_DOUBLE + capi._GRID_DOUBLE_B + capi._GRID_INT_A) \
-        + grid.brBusIdx.nbytes
+    if not partitioned:
+        solve_e2e()
+    info_e2e, t_e2e, e2e_split, lgrid = solve_e2e()
+    grid_bytes = sum(getattr(lgrid, n).nbytes for n in capi._GRID_DOUBLE + capi._GRID_DOUBLE_B + capi._GRID_INT_A) \
+        + lgrid.brBusIdx.nbytes
+    d2h_bytes = 8.0 * (2 * lgrid.ngen + 8 * lgrid.nline)
+    if dist is not None:
+        tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt[0])
+
+    # ---- partitioned: the same solve on ONE GPU (rank 0) must end identically --------------------------------------
+    parity = None
+    if partitioned and rank == 0:
+        gs1, keep1 = make_grid_struct(grid)
+        h1 = C.c_void_p()
+        check(lib.ea_create(C.byref(gs1), local_rank, C.byref(h1)))
+        check(lib.ea_init_solution(h1, rho_pq, rho_va), h1)
+        p1 = params_struct(par); i1 = EaInfo()
+        check(lib.ea_admm_two_level(h1, C.byref(p1), C.byref(i1)), h1)
+        lib.ea_destroy(h1)
+        parity = {"single_gpu": {"status": capi.STATUS_NAMES[i1.status], "outer": i1.outer, "cumul": i1.cumul, "objval": i1.objval,
+                                 "mismatch": i1.mismatch, "solver_time_s": i1.time_overall},
+                  "partitioned": {"status": capi.STATUS_NAMES[info_e2e.status], "outer": info_e2e.outer, "cumul": info_e2e.cumul,
+                                  "objval": info_e2e.objval, "mismatch": info_e2e.mismatch,
+                                  "solver_time_s": info_e2e.time_overall}}
+        same = (i1.status, i1.outer, i1.cumul) == (info_e2e.status, info_e2e.outer, info_e2e.cumul) and \
+            abs(i1.objval - info_e2e.objval) <= 1e-9 * abs(i1.objval)
+        parity["identical_counts_and_objective"] = bool(same)
+        if not same:
+            raise RuntimeError(f"bench.py: the {world}-GPU partitioned solve differs from the single-GPU solve: {parity}")
 
     # ---------------- device-resident throughput over K steps ------------------------------------
     class Driver:
         """admm_two_level control flow (admm_two_level.jl:29-77), resumable in slices of n iterations."""
 
-        def __init__(self, h):
+        def __init__(self, h, nline):
             self.h = h
+            self.nline = nline
             self.restarts = 0
             self.reset()
 
@@ -270,9 +362,9 @@ def run_ours(args, rank, world, local_rank):
                 if self.need_outer:
                     if self.solved or self.outer >= par.outer_iterlim:
                         check(lib.ea_init_solution(h, rho_pq, rho_va), h)
-                        z = np.zeros(grid.nline)
+                        z = np.zeros(self.nline)
                         for row in (25, 26, 27):
-                            check(lib.ea_set_membuf(h, row, dptr(z), grid.nline), h)
+                            check(lib.ea_set_membuf(h, row, dptr(z), self.nline), h)
                         self.restarts += 1
                         self.reset()
                     self.outer += 1
@@ -300,11 +392,10 @@ def run_ours(args, rank, world, local_rank):
 
     def trajectory(kernel_timing, sample_clocks, flush_mb=0):
         """init -> W warm-up iterations -> K timed iterations of the same solve trajectory."""
-        h = C.c_void_p()
-        check(lib.ea_create(C.byref(gs), local_rank, C.byref(h)))
+        mod, h, lg, _ = new_handle()
         check(lib.ea_init_solution(h, rho_pq, rho_va), h)
         check(lib.ea_set_option(h, b"count_work", 1.0 if kernel_timing else 0.0), h)
-        drv = Driver(h)
+        drv = Driver(h, lg.nline)
         drv.run(args.warmup)
         check(lib.ea_reset_counters(h), h)
         check(lib.ea_set_option(h, b"kernel_timing", float(kernel_timing)), h)
@@ -327,7 +418,7 @@ def run_ours(args, rank, world, local_rank):
         check(lib.ea_get_kernel_times(h, kt), h)      # CUDA events on the library's own stream
         cnt = EaCounters()
         check(lib.ea_get_counters(h, C.byref(cnt)), h)
-        lib.ea_destroy(h)
+        drop_handle(mod, h)
         return dict(ran=ran, wall=wall, kt=list(kt), cnt=cnt.as_dict(), clocks=clocks, restarts=drv.restarts)
 
     # Two passes over the same K iterations of the same trajectory:
@@ -344,10 +435,37 @@ def run_ours(args, rank, world, local_rank):
     t_res = A["kt"][0]               # device time inside ea_run_inner* (events around the enqueued chunks), pass A
     t_dev = B["kt"][2] + B["kt"][4]  # summed event-bracketed kernel time of the K iterations, pass B
     launches = int(A["kt"][1] + A["kt"][3] + A["kt"][5])
+    t_x_all = t_b_all = None
     if dist is not None:
-        tt = torch.tensor([t_dev, dt, t_res], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_dev, dt, t_res, B["kt"][2], B["kt"][4]], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, dt, t_res = float(tt[0]), float(tt[1]), float(tt[2])
+        t_dev, dt, t_res, t_x_all, t_b_all = (float(v) for v in tt)
+        tl = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        launches = int(tl[0])
+
+    # secondary (N > 1, partitioned mode): the round-1 weak-scaling figure - N independent load scenarios, no collective
+    replicas = None
+    if partitioned and not args.no_replicas:
+        gs_r, keep_r = make_grid_struct(scenario_grid(rank))
+        hr = C.c_void_p()
+        check(lib.ea_create(C.byref(gs_r), local_rank, C.byref(hr)))
+        check(lib.ea_init_solution(hr, rho_pq, rho_va), hr)
+        check(lib.ea_set_option(hr, b"count_work", 0.0), hr)
+        drv = Driver(hr, grid.nline)
+        drv.run(args.warmup)
+        check(lib.ea_reset_counters(hr), hr)
+        dist.barrier(); torch.cuda.synchronize()
+        ran_r = drv.run(args.steps)
+        torch.cuda.synchronize()
+        ktr = (C.c_double * 8)()
+        check(lib.ea_get_kernel_times(hr, ktr), hr)
+        lib.ea_destroy(hr)
+        tr = torch.tensor([ktr[0]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        replicas = {"value": world * ran_r / float(tr[0]), "unit": "iterations/s", "scaling": "weak",
+                    "what": f"{world} independent load scenarios (loads x U[0.99,1.01]), one per GPU, no collective; "
+                            "iterations back to back from the CUDA graph (as value_l2_resident)"}
 
     if rank != 0:
         if dist is not None:
@@ -369,33 +487,50 @@ def run_ours(args, rank, world, local_rank):
     #                  FP64 flops = 1645 per objective evaluation incl. its share of the TRON algebra
     #                  (ncu op counts / evaluations, profiles/r1_fp64_ops_per_launch.csv)
     #   bus kernel:    64 B per entry (u,z,lambda,rho,lz read; v,z,lambda written) + 48 B per bus + CSR pointers
-    x_bytes = 568.0 * grid.nline + 128.0 * grid.ngen
-    bus_bytes = 64.0 * nvar + 48.0 * grid.nbus + 8.0 * (grid.nbus + 1)
+    ln, gn, bn = lgrid.nline, lgrid.ngen, lgrid.nbus          # what ONE launch of this rank processes
+    x_bytes = 568.0 * ln + 128.0 * gn
+    bus_bytes = 64.0 * (2 * gn + 8 * ln) + 48.0 * bn + 8.0 * (bn + 1)
     evals = cnt["tron_evals"]
-    flops = 1645.0 * evals
+    # ALGORITHMIC flops: per objective evaluation f = 119; gradient + Hessian = 350 + 1006 at every accepted
+    # point and at the start of every TRON solve (the reference evaluates them there only); dtron per step (Cauchy search:
+    # 2 matrix-vector products + projections ~200, Cholesky 72, projected search ~150, model / norms ~100 = 522) and per
+    # CG iteration (1 matrix-vector product + 2 triangular solves = 144). Steps = evaluations - TRON solves.
+    n_gh = evals - cnt["rejected_steps"]
+    n_steps = max(evals - cnt["auglag_iters"], 0)
+    flops_alg = 119.0 * evals + 1356.0 * n_gh + 522.0 * n_steps + 144.0 * cnt["cg_iters"]
+    flops_exec = 1645.0 * evals       # executed DFMA x 2 + DMUL + DADD per evaluation (ncu, profiles/r1_fp64_ops_per_launch.csv)
     avg_x = t_x / n_x if n_x else float("nan")
     avg_b = t_b / n_b if n_b else float("nan")
-    roof = {   # dominant kernel of the step (share of the step below). It is neither HBM- nor tensor-bound: it is
-               # bound by the serial chain of the slowest branch; both rooflines are reported.
-        "kernel": "k_xupdate (generators + branch augmented-Lagrangian / TRON solves)", "bound": "hbm",
-        "achieved": x_bytes / avg_x / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": x_bytes / avg_x / 1e9 / hbm_peak,
-        "traffic": 45.5e6, "traffic_source": "ncu dram__bytes_read+write per launch (cold L2, as in the timed pass), profiles/r1_fp64_ops_per_launch.csv",
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": x_bytes, "avg_launch_us": 1e6 * avg_x,
-        "share_of_step": t_x / (t_x + t_b) if (t_x + t_b) else None,
-        "fp64": {"achieved_tflops": flops / t_x / 1e12 if t_x else None, "peak_tflops": fp64_peak.value,
-                 "frac": (flops / t_x / 1e12 / fp64_peak.value) if (t_x and fp64_peak.value) else None,
-                 "peak_source": "ea_diag_fp64_peak (8 independent DFMA chains/thread, measured in this run)",
-                 "flops_per_evaluation": 1645.0, "evaluations_per_launch": evals / n_x if n_x else None},
+    roof = {   # dominant kernel of the step. An FP64-pipe kernel by its arithmetic (nothing here is a contraction; 568 B per
+               # branch make it 2 % of the HBM roofline) - in fact bound by the serial chain of its slowest branch.
+        "kernel": "k_xupdate (generators + branch augmented-Lagrangian / TRON solves)", "bound": "fp64",
+        "achieved": flops_alg / t_x / 1e12 if t_x else None, "peak": fp64_peak.value, "unit": "TFLOP/s",
+        "frac": (flops_alg / t_x / 1e12 / fp64_peak.value) if (t_x and fp64_peak.value) else None,
+        "peak_source": "ea_diag_fp64_peak: 8 independent DFMA chains per thread, measured in this run (MEASURED_PEAKS.json has "
+                       "no FP64 figure)",
+        "algorithmic_flops_per_launch": flops_alg / n_x if n_x else None,
+        "algorithmic_flops": "119 nfev + 1356 ngev + 522 steps + 144 cg (SURVEY 8d; counters of this pass)",
+        "executed_flops_per_launch": flops_exec / n_x if n_x else None,
+        "frac_executed": (flops_exec / t_x / 1e12 / fp64_peak.value) if (t_x and fp64_peak.value) else None,
+        "traffic": 45.5e6, "traffic_source": "ncu dram__bytes_read+write per launch at the 1-GPU size (cold L2, as in the timed "
+                                            "pass), profiles/r1_fp64_ops_per_launch.csv",
+        "avg_launch_us": 1e6 * avg_x, "share_of_step": t_x / (t_x + t_b) if (t_x + t_b) else None,
+        "hbm": {"achieved": x_bytes / avg_x / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": x_bytes / avg_x / 1e9 / hbm_peak,
+                "algorithmic_bytes_per_launch": x_bytes, "peak_source": peak_src},
+        "evaluations_per_launch": evals / n_x if n_x else None,
         "critical_path": {"max_evaluations_of_one_branch": cnt["max_evals_lane"],
                           "mean_evaluations_per_branch": evals / max(cnt["line_calls"], 1),
-                          "note": "launch time ~ (evaluations of the slowest branch / 2) x ~7.5 us per serial TRON round"},
+                          "note": "launch time ~ evaluations of the slowest branch x ~5 us (one lane, serial; DESIGN.md section 6)"},
     }
     roof_bus = {"kernel": "k_bus<fused> (bus consensus + z + lambda + residual norms)", "bound": "hbm",
                 "achieved": bus_bytes / avg_b / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bus_bytes / avg_b / 1e9 / hbm_peak, "traffic": 31.9e6,
                 "traffic_source": "ncu dram bytes per launch (cold cache; the 50 MB working set is L2-resident in the loop)",
                 "algorithmic_bytes_per_launch": bus_bytes, "avg_launch_us": 1e6 * avg_b,
+                "peak_source": peak_src,
                 "share_of_step": t_b / (t_x + t_b) if (t_x + t_b) else None}
+    if partitioned:
+        roof_bus["kernel"] = "k_bus<fused> + exchange (peer stores / all-gather) + k_finish (ghost install, norms, termination)"
 
     # ---------------- CPU baseline (1 core, bounded sample) ----------------------------------------
     cpu = None
@@ -414,27 +549,82 @@ def run_ours(args, rank, world, local_rank):
                "sample": f"first {n_cpu} inner iterations of the same solve on the full grid, serial loops "
                          f"(oracle restatement of the reference's use_gpu=false path, not Julia)"}
 
-    value = world * ran / t_dev if t_dev > 0 else None
+    # ---------------- BASELINE configs 2 and 3 in the same line (1 GPU): whole solves ---------------------------
+    other = None
+    if world == 1 and not args.no_other_configs and args.workload == "ACTIVSg70k":
+        other = {}
+        # (outer, inner) budget: the README's rho of the pegase files stalls on the synthetic stand-ins and the
+        # stalled regime is slow (thousands of branches walk the whole penalty ladder every iteration): 3 x 300 there
+        for name, wl, rpq, rva, budget in (("config2_case1354pegase", "case1354pegase", 1e1, 1e3, (3, 300)),
+                                           ("config2_case1354pegase_converging_rho", "case1354pegase", 4e2, 4e4, (20, 1000)),
+                                           ("config3_case13659pegase", "case13659pegase", 5e1, 5e3, (3, 300))):
+            g2, _ = make_grid(wl)
+            p2, _, _ = default_params(wl)
+            p2.outer_iterlim, p2.inner_iterlim = budget
+            gs2, keep2 = make_grid_struct(g2)
+            best = None
+            for rep in range(2):
+                h2 = C.c_void_p()
+                t0 = time.perf_counter()
+                check(lib.ea_create(C.byref(gs2), local_rank, C.byref(h2)))
+                check(lib.ea_init_solution(h2, rpq, rva), h2)
+                ps = params_struct(p2); i2 = EaInfo()
+                check(lib.ea_admm_two_level(h2, C.byref(ps), C.byref(i2)), h2)
+                u2 = np.empty(2 * g2.ngen + 8 * g2.nline)
+                check(lib.ea_get_vector(h2, 0, dptr(u2), u2.size), h2)
+                t = time.perf_counter() - t0
+                lib.ea_destroy(h2)
+                if best is None or t < best[0]:
+                    best = (t, i2)
+            t, i2 = best
+            st = capi.STATUS_NAMES[i2.status]
+            other[name] = {"workload": f"{wl}-like synthetic grid", "nbus": g2.nbus, "nline": g2.nline, "rho_pq": rpq, "rho_va": rva,
+                           "scale": p2.scale, "outer_iterlim": budget[0], "inner_iterlim": budget[1], "status": st, "outer": i2.outer, "cumul": i2.cumul, "objval": i2.objval,
+                           "iterations_per_s_e2e": i2.cumul / t, "seconds_e2e": t,
+                           "time_to_converge_s": t if st == "Solved" else None,
+                           "note": None if st == "Solved" else "the README's rho for the real pegase file stalls on the synthetic "
+                                   "stand-in (oracle alike, SURVEY 8d): throughput over a 3 x 300 budget"}
+
+    window = (f"inner iterations {args.warmup + 1}-{args.warmup + args.steps} of the solve trajectory from the flat start "
+              f"(12 outer / 447 inner in all; the first ~10 inner iterations of every outer iteration restart the penalty "
+              f"ladder and are the expensive ones: a short window early in the solve, like the driver's --steps 20 --warmup 5, "
+              f"measures that regime; steady state is ~1.5x faster)")
+    value = (ran if partitioned else world * ran) / t_dev if t_dev > 0 else None
+    if world == 1:
+        parallelism = "1 GPU"
+    elif partitioned:
+        parallelism = (f"ONE solve bus-partitioned over {world} GPUs (graph cut: {part_info['cut']['cut_lines']} of {grid.nline} "
+                       f"branches cut and solved redundantly), one exchange per inner iteration by "
+                       + ("peer-memory stores over NVLink fused into the bus kernel" if args.exchange == "peer"
+                          else "ncclAllGather on the library's stream"))
+    else:
+        parallelism = f"{world} independent load scenarios (loads x U[0.99,1.01]), one per GPU, no collective"
+    e2e_mult = 1 if (partitioned or world == 1) else world
     line = {
         "metric": "admm_inner_iterations_per_sec", "value": value, "unit": "iterations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / ran,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if partitioned else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
         "config": {**base_config(args.workload, grid, par, rho_pq, rho_va),
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent load scenarios (loads x U[0.99,1.01]), one per GPU, no collective",
+                   "parallelism": parallelism,
+                   "timed_window": window,
                    "l2_policy": f"L2 flushed between timed iterations: a {FLUSH_MB} MB write precedes every iteration (the "
                                 "100 MB working set - 15 vectors x 5.8 MB + grid - would otherwise stay in the 126 MB L2); "
                                 "value = K / (sum of the CUDA-event times of the two kernels of each iteration, flush "
                                 "outside the brackets); value_l2_resident = the same K iterations back to back from the "
                                 "CUDA graph, no flush, no per-kernel events (what a solve sees)",
                    "restarts_in_timed_region": A["restarts"]},
-        "value_l2_resident": world * ran / t_res if t_res > 0 else None,
+        "value_l2_resident": (ran if partitioned else world * ran) / t_res if t_res > 0 else None,
         "ms_per_step_l2_resident": 1e3 * t_res / ran,
         "wall_ms_per_step": 1e3 * dt / ran,
         "gpu_launches": launches,
         "clocks": clocks,
-        "e2e": {"value": world * info_e2e.cumul / t_e2e, "unit": "iterations/s",
-                "h2d_bytes_per_step": grid_bytes / max(info_e2e.cumul, 1), "d2h_bytes_per_step": 8.0 * nvar / max(info_e2e.cumul, 1),
-                "what": "ea_create(host grid arrays) + ea_init_solution + ea_admm_two_level + ea_get_vector(u) ; wall clock",
+        "e2e": {"value": e2e_mult * info_e2e.cumul / t_e2e, "unit": "iterations/s",
+                "h2d_bytes_per_step": grid_bytes / max(info_e2e.cumul, 1), "d2h_bytes_per_step": d2h_bytes / max(info_e2e.cumul, 1),
+                "what": ("ea_create(host grid arrays of the rank's part) + ea_set_partition + ea_init_solution + ea_admm_two_level + "
+                         "ea_get_vector(u); max over ranks; the handle's NCCL communicator / IPC mapping (comm_setup_s, one-off per "
+                         "process group) is timed separately and not included; h2d / d2h bytes are per rank") if partitioned else
+                        "ea_create(host grid arrays) + ea_init_solution + ea_admm_two_level + ea_get_vector(u) ; wall clock",
                 "time_to_converge_s": t_e2e, "solver_time_s": info_e2e.time_overall, "split": e2e_split,
                 "status": capi.STATUS_NAMES[info_e2e.status], "outer": info_e2e.outer, "cumul": info_e2e.cumul,
                 "objval": info_e2e.objval, "mismatch": info_e2e.mismatch},
@@ -443,6 +633,14 @@ def run_ours(args, rank, world, local_rank):
         "work_counters": cnt,
         "cpu_baseline": cpu,
     }
+    if partitioned:
+        line["partition"] = {**part_info, "local_lines_rank0": lgrid.nline, "local_buses_rank0": lgrid.nbus,
+                             "x_update_us_max_over_ranks": 1e6 * t_x_all / n_x if n_x else None,
+                             "bus_exchange_finish_us_max_over_ranks": 1e6 * t_b_all / n_b if n_b else None}
+        line["partition_parity"] = parity
+        line["replicas"] = replicas
+    if other is not None:
+        line["other_configs"] = other
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -457,6 +655,12 @@ def main():
     ap.add_argument("--workload", default="ACTIVSg70k", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="partitioned", choices=["partitioned", "replicas"],
+                    help="N > 1: one bus-partitioned solve over the N GPUs (strong scaling) or N independent load scenarios")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="partitioned mode: per-iteration exchange by peer-memory stores (CUDA IPC over NVLink) or ncclAllGather")
+    ap.add_argument("--no-replicas", action="store_true", help="partitioned mode: skip the secondary weak-scaling measurement")
+    ap.add_argument("--no-other-configs", action="store_true", help="1 GPU: skip the whole solves of BASELINE configs 2 and 3")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

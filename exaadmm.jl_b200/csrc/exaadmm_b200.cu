@@ -723,13 +723,16 @@ int ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_
     int rc = sync_ctrl_to_device(h, beta, eps_pri, inner_start, inner_limit);
     if (rc) return rc;
     int64_t enq = inner_start;
-    const bool graph = h->use_graph && !h->kernel_timing && !h->d.partitioned && chunk > 1 && inner_limit - inner_start >= chunk;
+    // (partitioned handles too: the exchange is part of the chunk - peer stores inside the bus kernel, or the captured
+    //  ncclAllGather; every rank replays the same graph, launches after `done` are no-ops on every rank alike)
+    const bool graph = h->use_graph && !h->kernel_timing && !h->loopback && chunk > 1 && inner_limit - inner_start >= chunk;
     if (graph && (rc = build_loop_graph(h, chunk, max_auglag, mu_max, scale))) return rc;
     for (;;) {
         const int64_t todo = graph ? chunk : std::min<int64_t>(chunk, inner_limit - enq);
         if (graph) {
             CK(cudaGraphLaunch(h->graph, h->stream));
             h->n_replay++; h->n_x += chunk; h->n_bus += chunk;
+            if (h->d.partitioned) h->n_other += chunk;                 // k_finish
         } else {
             for (int64_t i = 0; i < todo; ++i)
                 if ((rc = enqueue_iteration(h, max_auglag, mu_max, scale, (int)i))) return rc;

@@ -441,7 +441,9 @@ __device__ __forceinline__ void bus_gen_gather(const Dev &d, const double *zold,
 __device__ __forceinline__ BusSolve bus_solve(const Dev &d, int b, double common_wi, double common_ti, double inv_p,
                                               double inv_q, double rs_w, double rs_t, double rhs1, double rhs2,
                                               double inv_pg, double inv_qg) {
-    const double irw = tron::ddiv(1.0, rs_w);
+    // (a bus without branch ends has rs_w = 0: IEEE division, so that the outcome is the reference's (NaN / inf) rather
+    //  than whatever the refined reciprocal makes of a zero divisor)
+    const double irw = (rs_w > 0.0) ? tron::ddiv(1.0, rs_w) : 1.0 / rs_w;
     common_wi = quot(common_wi, rs_w, irw);
     const double gr = d.YshR[b], gi = d.YshI[b];
     rhs1 -= gr * common_wi;
@@ -455,7 +457,7 @@ __device__ __forceinline__ BusSolve bus_solve(const Dev &d, int b, double common
     s.mu2 = tron::ddiv(rhs2 - quot(A21, A11, iA11) * rhs1, A22 - quot(A21, A11, iA11) * A12);
     s.mu1 = quot(rhs1 - A12 * s.mu2, A11, iA11);
     s.wi = common_wi + quot(gr * s.mu1 - gi * s.mu2, rs_w, irw);
-    s.ti = tron::ddiv(common_ti, rs_t);
+    s.ti = (rs_t > 0.0) ? tron::ddiv(common_ti, rs_t) : common_ti / rs_t;
     return s;
 }
 

