@@ -187,9 +187,7 @@ def _subgrid(g: GridData, bus_ids: np.ndarray, line_ids: np.ndarray, gen_ids: np
     two[0::2] = 2 * line_ids
     two[1::2] = 2 * line_ids + 1
     # generator -> bus from the global CSR
-    gen_bus_global = np.empty(g.ngen, dtype=np.int64)
-    for b in range(g.nbus):
-        gen_bus_global[g.GenIdx[g.GenStart[b] - 1:g.GenStart[b + 1] - 1] - 1] = b
+    gen_bus_global = _gen_bus(g)
     gb = gmap[gen_bus_global[gen_ids]] if len(gen_ids) else np.zeros(0, dtype=np.int64)
     fr_start, fr_idx = _csr_1based(fr, nb)
     to_start, to_idx = _csr_1based(to, nb)
@@ -215,28 +213,39 @@ def _subgrid(g: GridData, bus_ids: np.ndarray, line_ids: np.ndarray, gen_ids: np
     )
 
 
-def build_local_grids(grid: GridData, part: np.ndarray) -> list[LocalGrid]:
-    """All ranks' local grids (each rank only needs its own; building all is cheap and lets
-    tests check global consistency)."""
+def _gen_bus(g: GridData) -> np.ndarray:
+    """bus (0-based) of every generator, from the bus -> generator CSR."""
+    gen_bus = np.empty(g.ngen, dtype=np.int64)
+    gen_bus[np.asarray(g.GenIdx, dtype=np.int64) - 1] = np.repeat(np.arange(g.nbus, dtype=np.int64), np.diff(g.GenStart))
+    return gen_bus
+
+
+def build_local_grids(grid: GridData, part: np.ndarray, only: int | None = None) -> list[LocalGrid]:
+    """The ranks' local grids. `only`: build just that rank's (what a rank of a multi-GPU job needs; the list then
+    holds None for the others); building all lets the tests check global consistency."""
     nparts = int(part.max()) + 1
     fbus = grid.brBusIdx[0::2] - 1
     tbus = grid.brBusIdx[1::2] - 1
     fpart, tpart = part[fbus], part[tbus]
-    gen_bus = np.empty(grid.ngen, dtype=np.int64)
-    for b in range(grid.nbus):
-        gen_bus[grid.GenIdx[grid.GenStart[b] - 1:grid.GenStart[b + 1] - 1] - 1] = b
+    gen_bus = _gen_bus(grid)
     cut = np.flatnonzero(fpart != tpart)
-    # send list of rank r: owned ends of cut branches, ordered by (global line, end)
-    send_lists = []
+    # send list of rank r: owned ends of cut branches, ordered by (global line, end); key = 2 * line + end
+    cut_keys = np.concatenate([2 * cut, 2 * cut + 1])
+    cut_owner = np.concatenate([fpart[cut], tpart[cut]])
+    order = np.argsort(cut_keys, kind="stable")
+    cut_keys, cut_owner = cut_keys[order], cut_owner[order]
+    send_keys = [cut_keys[cut_owner == r] for r in range(nparts)]
+    send_counts = np.array([len(k) for k in send_keys], dtype=np.int64)
+    # position of every cut-branch end in its owner's send list
+    pos_of_key = np.empty(len(cut_keys), dtype=np.int64)
     for r in range(nparts):
-        ends = [(int(l), 0) for l in cut if fpart[l] == r] + [(int(l), 1) for l in cut if tpart[l] == r]
-        ends.sort()
-        send_lists.append(ends)
-    send_pos = [{e: k for k, e in enumerate(lst)} for lst in send_lists]
-    send_counts = np.array([len(lst) for lst in send_lists], dtype=np.int64)
+        pos_of_key[cut_owner == r] = np.arange(send_counts[r])
 
     out = []
     for r in range(nparts):
+        if only is not None and r != only:
+            out.append(None)
+            continue
         owned = np.flatnonzero(part == r)
         lines = np.flatnonzero((fpart == r) | (tpart == r))
         ghosts = np.unique(np.concatenate([tbus[lines][tpart[lines] != r], fbus[lines][fpart[lines] != r]])) \
@@ -260,21 +269,24 @@ def build_local_grids(grid: GridData, part: np.ndarray) -> list[LocalGrid]:
             owned_entry[base_l[f_own] + k] = True
         for k in TO_POS:
             owned_entry[base_l[t_own] + k] = True
-        lmap = {int(gl): k for k, gl in enumerate(lines)}
-        s_line = np.array([lmap[l] for l, _ in send_lists[r]], dtype=np.int64)
-        s_end = np.array([e for _, e in send_lists[r]], dtype=np.int64)
-        g_line, g_end, g_rank, g_pos = [], [], [], []
-        for k, gl in enumerate(lines):
-            if fpart[gl] != r:
-                g_line.append(k); g_end.append(0); g_rank.append(int(fpart[gl])); g_pos.append(send_pos[fpart[gl]][(int(gl), 0)])
-            if tpart[gl] != r:
-                g_line.append(k); g_end.append(1); g_rank.append(int(tpart[gl])); g_pos.append(send_pos[tpart[gl]][(int(gl), 1)])
+        # local index of a global line (lines is sorted)
+        sk = send_keys[r]
+        s_line = np.searchsorted(lines, sk // 2).astype(np.int64)
+        s_end = (sk % 2).astype(np.int64)
+        # ghost ends, ordered by (local line, end): ends of this rank's lines owned by another rank
+        loc = np.arange(len(lines), dtype=np.int64)
+        gk_local = np.concatenate([2 * loc[~f_own], 2 * loc[~t_own] + 1])
+        gk_global = np.concatenate([2 * lines[~f_own], 2 * lines[~t_own] + 1])
+        gk_rank = np.concatenate([fpart[lines][~f_own], tpart[lines][~t_own]])
+        o = np.argsort(gk_local, kind="stable")
+        gk_local, gk_global, gk_rank = gk_local[o], gk_global[o], gk_rank[o]
+        g_pos = pos_of_key[np.searchsorted(cut_keys, gk_global)] if len(gk_global) else np.zeros(0, dtype=np.int64)
         out.append(LocalGrid(
             rank=r, nparts=nparts, grid=lg, n_owned_bus=len(owned), bus_global=buses, line_global=lines,
             gen_global=gens, owned_entry=owned_entry, entry_global=entry_global,
             send_line=s_line, send_end=s_end,
-            ghost_line=np.array(g_line, dtype=np.int64), ghost_end=np.array(g_end, dtype=np.int64),
-            ghost_src_rank=np.array(g_rank, dtype=np.int64), ghost_src_pos=np.array(g_pos, dtype=np.int64),
+            ghost_line=(gk_local // 2).astype(np.int64), ghost_end=(gk_local % 2).astype(np.int64),
+            ghost_src_rank=gk_rank.astype(np.int64), ghost_src_pos=g_pos.astype(np.int64),
             send_counts=send_counts,
             stats={"owned_buses": len(owned), "ghost_buses": len(ghosts), "lines": len(lines),
                    "cut_lines": int(np.sum(fpart[lines] != tpart[lines])), "gens": len(gens)}))

@@ -40,7 +40,7 @@ def torch_nccl_path() -> str | None:
 
 def make_partitioned_model(env: AdmmEnv, grid: GridData, part: np.ndarray, rank: int) -> tuple[ModelAcopf, LocalGrid]:
     """ModelAcopf on the rank-local grid + ea_set_partition."""
-    lg = build_local_grids(grid, part)[rank]
+    lg = build_local_grids(grid, part, only=rank)[rank]
     mod = ModelAcopf(env, grid=lg.grid)
     keep = [np.ascontiguousarray(a, dtype=np.int64) for a in
             (lg.send_line, lg.send_end, lg.ghost_line, lg.ghost_end, lg.ghost_src_rank, lg.ghost_src_pos)]
