@@ -212,6 +212,99 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------
+def scenario_block(workload, ids, local_rank, budget, oracle_check=True):
+    """BASELINE config 5 on ONE GPU: the load scenarios `ids` of `workload` (every Pd, Qd x iid U[0.95, 1.05], seed
+    nbus + s) solved (a) concurrently as stand-alone solves, one CUDA stream and one host thread each - other
+    scenarios' kernels fill the SMs a solve leaves idle while its slowest branch finishes -, (b) as ONE batch
+    (ea_batch_*: one branch kernel over all (scenario, branch) pairs, per-scenario termination), (c) one after the other.
+    Whole solves with an (outer, inner) budget; returns iterations/s of each and the per-scenario outcomes."""
+    from exaadmm_b200.scenarios import ScenarioBatch, solve_scenarios, scenario_loads
+    grid_base, data = make_grid(workload)
+    par, rho_pq, rho_va = default_params(workload)
+    kw = dict(scale=par.scale, outer_iterlim=budget[0], inner_iterlim=budget[1])
+    out = {"workload": f"{workload}-like synthetic grid, {len(ids)} load scenarios on this GPU (loads x U[0.95,1.05], seed nbus + s)",
+           "rho_pq": rho_pq, "rho_va": rho_va, "scale": par.scale, "outer_iterlim": budget[0], "inner_iterlim": budget[1]}
+    best = {}
+    for name, conc in (("concurrent_streams", len(ids)), ("sequential", 1)):
+        for rep in range(2 if name == "concurrent_streams" else 1):
+            res, wall = solve_scenarios(data, ids, rho_pq=rho_pq, rho_va=rho_va, tight_factor=0.99, max_concurrent=conc,
+                                        gpu_no=local_rank, **kw)
+            cum = [int(m.info.cumul) for _, m in res]
+            st = [m.info.status for _, m in res]
+            obj0 = res[0][1].info.objval
+            for _, m in res:
+                m.close()
+            if name not in best or wall < best[name][0]:
+                best[name] = (wall, cum, st, obj0)
+    for rep in range(2):
+        b = ScenarioBatch(data, ids, rho_pq=rho_pq, rho_va=rho_va, tight_factor=0.99, gpu_no=local_rank)
+        wall = b.solve(**kw)
+        cum = [int(m.info.cumul) for m in b.models]
+        st = [m.info.status for m in b.models]
+        obj0 = b.models[0].info.objval
+        b.close()
+        if "batched" not in best or wall < best["batched"][0]:
+            best["batched"] = (wall, cum, st, obj0)
+    for name, (wall, cum, st, obj0) in best.items():
+        out[name] = {"iterations_per_s": sum(cum) / wall, "seconds": wall, "iterations": sum(cum),
+                     "solved": st.count("Solved"), "cumul_min": min(cum), "cumul_max": max(cum)}
+    out["same_iteration_counts_in_all_three"] = best["batched"][1] == best["concurrent_streams"][1] == best["sequential"][1]
+    if oracle_check:
+        from oracle.oracle import OracleModel
+        par.outer_iterlim, par.inner_iterlim = budget
+        om = OracleModel(grid_base, par, rho_pq, rho_va)
+        om.set_threads(os.cpu_count() or 1)
+        Pd, Qd = scenario_loads(grid_base, ids[0])
+        om.set_load(Pd, Qd)
+        oi = om.admm_two_level()
+        out["oracle_check_scenario0"] = {"cumul_equal": int(oi.cumul) == best["batched"][1][0],
+                                         "objective_rel_diff": abs(best["batched"][3] - oi.objval) / abs(oi.objval)}
+    return out
+
+
+def run_scenarios(args, rank, world, local_rank):
+    """--scenarios S: config 5 as the headline of the line - S scenarios sharded over the ranks (rank r takes r, r+N, ...)."""
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ids = list(range(rank, args.scenarios, world))
+    blk = scenario_block(args.workload, ids, local_rank, (args.scenario_outer, args.scenario_inner), oracle_check=(rank == 0))
+    its = torch.tensor([blk["concurrent_streams"]["iterations"], blk["batched"]["iterations"]], dtype=torch.float64, device="cuda")
+    tm = torch.tensor([blk["concurrent_streams"]["seconds"], blk["batched"]["seconds"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(its, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        grid, _ = make_grid(args.workload)
+        par, rho_pq, rho_va = default_params(args.workload)
+        v_streams, v_batch = float(its[0] / tm[0]), float(its[1] / tm[1])
+        line = {"metric": "admm_inner_iterations_per_sec", "value": max(v_streams, v_batch), "unit": "iterations/s", "n_gpus": world,
+                "value_method": "batched (ea_batch_*)" if v_batch >= v_streams else "concurrent stand-alone solves",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / max(v_streams, v_batch), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {**base_config(args.workload, grid, par, rho_pq, rho_va),
+                           "outer_iterlim": args.scenario_outer, "inner_iterlim": args.scenario_inner,
+                           "parallelism": f"{args.scenarios} load scenarios sharded over {world} GPU(s) ({len(ids)} on rank 0), whole "
+                                          "solves; per GPU either one batch (one branch kernel over all (scenario, branch) "
+                                          "pairs) or concurrent stand-alone solves (one stream + host thread each); no "
+                                          "data-path collective",
+                           "l2_policy": "whole solves back to back (the scenarios' working sets together exceed nothing: "
+                                        "64 x 4.5 MB at 2869 buses - L2 resident, as in production)"},
+                "value_batched": v_batch, "value_concurrent_streams": v_streams,
+                "e2e": {"value": max(v_streams, v_batch), "unit": "iterations/s", "what": "wall clock of the solves incl. the D2H "
+                        "of control blocks / norms; model creation (H2D) excluded",
+                        "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 32},
+                "gpu_launches": int(2 * float(its[0])),
+                "scenario_block_rank0": blk}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
     from exaadmm_b200 import capi
@@ -585,6 +678,11 @@ def run_ours(args, rank, world, local_rank):
                            "note": None if st == "Solved" else "the README's rho for the real pegase file stalls on the synthetic "
                                    "stand-in (oracle alike, SURVEY 8d): throughput over a 3 x 300 budget"}
 
+    config5 = None
+    if world == 1 and not args.no_other_configs and args.workload == "ACTIVSg70k":
+        # what ONE GPU does in BASELINE config 5 (64 scenarios of case2869pegase over 8 GPUs): 8 scenarios
+        config5 = scenario_block("case2869pegase", list(range(8)), local_rank, (3, 300))
+
     window = (f"inner iterations {args.warmup + 1}-{args.warmup + args.steps} of the solve trajectory from the flat start "
               f"(12 outer / 447 inner in all; the first ~10 inner iterations of every outer iteration restart the penalty "
               f"ladder and are the expensive ones: a short window early in the solve, like the driver's --steps 20 --warmup 5, "
@@ -641,6 +739,8 @@ def run_ours(args, rank, world, local_rank):
         line["replicas"] = replicas
     if other is not None:
         line["other_configs"] = other
+    if config5 is not None:
+        line["config5_scenarios_8_of_64_per_gpu"] = config5
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -660,7 +760,11 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="partitioned mode: per-iteration exchange by peer-memory stores (CUDA IPC over NVLink) or ncclAllGather")
     ap.add_argument("--no-replicas", action="store_true", help="partitioned mode: skip the secondary weak-scaling measurement")
-    ap.add_argument("--no-other-configs", action="store_true", help="1 GPU: skip the whole solves of BASELINE configs 2 and 3")
+    ap.add_argument("--no-other-configs", action="store_true", help="1 GPU: skip the whole solves of BASELINE configs 2, 3 and 5")
+    ap.add_argument("--scenarios", type=int, default=0,
+                    help="BASELINE config 5 as the headline: this many load scenarios of --workload, sharded over the GPUs")
+    ap.add_argument("--scenario-outer", type=int, default=3)
+    ap.add_argument("--scenario-inner", type=int, default=300)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -668,6 +772,8 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.scenarios > 0:
+        run_scenarios(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

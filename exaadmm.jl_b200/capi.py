@@ -233,6 +233,16 @@ SIGNATURES = {
     "ea_qp_set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
     "ea_qp_get_counters": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "ea_qp_get_kernel_times": (C.c_int, [_H, _pd]),
+    # batch of independent load scenarios
+    "ea_batch_last_error": (C.c_char_p, [_H]),
+    "ea_batch_create": (C.c_int, [C.POINTER(EaGrid), C.c_int, C.c_int32, _pd, _pd, C.POINTER(_H)]),
+    "ea_batch_destroy": (None, [_H]),
+    "ea_batch_size": (C.c_int32, [_H]),
+    "ea_batch_scenario": (_H, [_H, C.c_int32]),
+    "ea_batch_init_solution": (C.c_int, [_H, C.c_double, C.c_double]),
+    "ea_batch_admm_two_level": (C.c_int, [_H, C.POINTER(EaParams), C.POINTER(EaInfo)]),
+    "ea_batch_set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
+    "ea_batch_get_times": (C.c_int, [_H, _pd]),
     "ea_diag_fp64_peak": (C.c_int, [C.c_int, _pd]),
     "ea_diag_branch_eval": (C.c_int, [C.c_int, C.c_int64, _pd, _pd, _pd, C.c_double, _pd, _pd, _pd]),
     "ea_diag_branch_solve": (C.c_int, [C.c_int, C.c_int, C.c_int64, _pd, C.c_int32, C.c_double, C.c_double, _pd,

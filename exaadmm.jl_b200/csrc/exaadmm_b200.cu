@@ -1232,3 +1232,4 @@ int ea_diag_fp64_peak(int device, double *tflops) {
 
 #include "mp_host.inc"
 #include "qp_host.inc"
+#include "batch_host.inc"

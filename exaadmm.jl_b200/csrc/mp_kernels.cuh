@@ -88,21 +88,38 @@ k_mp_gen(MpDev m, branch::PowTable T, long long major_arg, int zsel_arg, int max
 // (period, branch) pairs, so the device sees T times the work of a single-period launch and ONE tail
 // (the serial chain of the slowest branch) instead of T. Same lane state machine as k_xupdate
 // (kernels.cuh); only the bookkeeping of which period a lane's branch belongs to is added.
+//
+// BATCH = true: the T models are independent load scenarios of one grid (BASELINE config 5; rolling-horizon style load
+// swaps, acopf_admm_rolling_gpu.jl:42-43) instead of coupled periods. Every scenario has its own loop control block
+// (inner counter, z selector, done flag: they converge at different iterations), `active` lists the scenarios still
+// iterating; the queue then runs over n_active x nline pairs, and the closed-form generator update of those scenarios
+// is done here too (k_mp_gen belongs to the coupled model).
 // ---------------------------------------------------------------------------
+struct BatchView { const int *active; const int *n_active; int ngen; };
+
+template <bool BATCH>
 __global__ void __launch_bounds__(XBLOCK, EA_XMINB)
-k_xupdate_mp(MpDev m, int nline, branch::PowTable T, long long major_arg, int zsel_arg, int max_auglag, double mu_max,
-             double scale) {
+k_xupdate_mp(MpDev m, BatchView bv, int nline, branch::PowTable T, long long major_arg, int zsel_arg, int max_auglag,
+             double mu_max, double scale) {
     extern __shared__ double tile[];                       // TILE_ROWS x XBLOCK
     long long major = major_arg;
     int zsel = zsel_arg;
-    if (major_arg == 0) {
+    int n_models = m.T;
+    if (BATCH) {
+        n_models = *bv.n_active;
+        if (n_models == 0) return;
+        for (int k = blockIdx.x * XBLOCK + threadIdx.x; k < n_models * bv.ngen; k += gridDim.x * XBLOCK) {
+            const Dev &d = m.devs[bv.active[k / bv.ngen]];
+            if (!d.ctrl->done) generator_update(d, d.zbuf[d.ctrl->zsel], k % bv.ngen);
+        }
+    } else if (major_arg == 0) {
         if (m.ctrl->done) return;
         major = m.ctrl->inner + 1;
         zsel = m.ctrl->zsel;
     }
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int total = m.T * nline;
+    const int total = n_models * nline;
     double *col = tile + threadIdx.x;
     const branch::Objective<branch::TileView<XBLOCK>> eval{ { col }, scale };
     branch::Lane L;
@@ -130,18 +147,25 @@ k_xupdate_mp(MpDev m, int nline, branch::PowTable T, long long major_arg, int zs
                 if (need) {
                     G = base + __popc(mk & ((1u << lane) - 1u));
                     if (G < total) {
-                        const int t = G / nline;
+                        const int a = G / nline;
+                        const int t = BATCH ? bv.active[a] : a;
                         const Dev &d = m.devs[t];
-                        load_branch(d, d.zbuf[zsel], G - t * nline, major, col, L);
-                        branch::begin(L, T);
+                        bool skip = false;
+                        if (BATCH) {
+                            // a scenario that finished earlier in this chunk of launches stays in the list until the
+                            // host has seen it: its branches are skipped (the lane takes another pair next time round)
+                            skip = d.ctrl->done != 0;
+                            major = d.ctrl->inner + 1; zsel = d.ctrl->zsel;
+                        }
+                        if (!skip) { load_branch(d, d.zbuf[zsel], G - a * nline, major, col, L); branch::begin(L, T); }
                     } else L.phase = branch::DONE;
                 }
             }
             double xl[6], xu[6];
             load_bounds(col, xl, xu);
             if (branch::eval_pass(L, eval, pass, xl, xu, max_auglag, mu_max, T)) {
-                const int t = G / nline;
-                store_branch(m.devs[t], G - t * nline, L);
+                const int a = G / nline;
+                store_branch(m.devs[BATCH ? bv.active[a] : a], G - a * nline, L);
                 work[0] += 1; work[1] += L.it_al; work[2] += L.evals; work[3] += L.cg; work[4] += L.shifts;
                 work[5] += L.rejected; work[6] += L.hit_max;
                 mx = max(mx, L.evals);
@@ -317,4 +341,12 @@ __global__ void k_mp_permute(int n, const int *gen_of_slot, const double *src, d
     else dst[k] = src[gen_of_slot[k]];
 }
 
+}  // namespace ea
+
+namespace ea {
+// scenario batch: the control blocks of all scenarios into one array (one D2H copy per chunk of iterations)
+__global__ void k_gather_ctrl(int n, Ctrl *const *pctrl, Ctrl *out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) out[s] = *pctrl[s];
+}
 }  // namespace ea

@@ -383,6 +383,27 @@ int  ea_qp_get_counters(ea_qp_handle_t *h, int64_t out[4]);
 /* out = { device seconds inside ea_qp_admm_one_level, iterations executed there, kernels launched, graph replays } */
 int  ea_qp_get_kernel_times(ea_qp_handle_t *h, double out[4]);
 
+/* ---- batch of independent load scenarios of one grid (BASELINE config 5) ---------------------------------------------
+ * The reference has no batched solve: it runs solve_acopf per scenario, swapping loads into a model the way its rolling
+ * horizon driver does (src/models/acopf/acopf_admm_rolling_gpu.jl:42-43). Here S scenarios of one grid are solved
+ * TOGETHER on one device: every scenario is an ordinary model (ea_batch_scenario returns its handle - borrowed, do not
+ * destroy - so `mod.solution`, membuf etc. are the single-model accessors) whose iterates are those of a stand-alone
+ * solve, bit for bit; the scenarios share the launches (one branch kernel over all (scenario, branch) pairs of the
+ * scenarios still iterating, one bus kernel with a termination test per scenario). Pd, Qd: S x nbus, MW / MVAr. */
+typedef struct ea_batch_handle ea_batch_handle_t;
+const char *ea_batch_last_error(const ea_batch_handle_t *h);   /* h may be NULL: last ea_batch_create error */
+int  ea_batch_create(const ea_grid_t *grid, int device, int32_t S, const double *Pd, const double *Qd,
+                     ea_batch_handle_t **out);
+void ea_batch_destroy(ea_batch_handle_t *h);
+int32_t ea_batch_size(const ea_batch_handle_t *h);
+ea_handle_t *ea_batch_scenario(ea_batch_handle_t *h, int32_t s);
+int  ea_batch_init_solution(ea_batch_handle_t *h, double rho_pq, double rho_va);       /* init_solution! of every scenario */
+/* admm_two_level (src/algorithms/admm_two_level.jl:1-88) of every scenario; infos: S entries (mod.info per scenario;
+ * time_overall = the batch's wall time). */
+int  ea_batch_admm_two_level(ea_batch_handle_t *h, const ea_params_t *par, ea_info_t *infos);
+int  ea_batch_set_option(ea_batch_handle_t *h, const char *name, double value);        /* "chunk", "use_graph" */
+int  ea_batch_get_times(ea_batch_handle_t *h, double out[2]);      /* device seconds inside ea_batch_admm_two_level, launches */
+
 int  ea_get_counters(ea_handle_t *h, ea_counters_t *out);
 int  ea_reset_counters(ea_handle_t *h);
 /* Options: "count_work" (0/1, atomics for ea_counters_t in the branch kernel, default 1),

@@ -523,3 +523,41 @@ def test_hardest_branches_of_a_real_solve_device_vs_host_build():
     assert np.mean(work[:, 1] == work0[:, 1]) >= 0.97                         # evaluations (libdevice vs libm sincos)
     same = work[:, 1] == work0[:, 1]
     np.testing.assert_allclose(sol[same, :10], sol0[same, :10], rtol=0, atol=1e-6)
+
+
+def test_scenario_batch_equals_stand_alone_solves_and_oracle():
+    """BASELINE config 5 in the small: load scenarios of one grid solved together (ea_batch_*: one branch kernel over the
+    (scenario, branch) pairs, per-scenario termination) must reproduce the stand-alone solve of every scenario bit for
+    bit - the scenarios converge after different numbers of iterations - and match the oracle on the same loads."""
+    from exaadmm_b200.scenarios import ScenarioBatch, scenario_loads
+    case = synthetic_case(300, 40, 420, seed=300)
+    ids = [0, 1, 2, 3, 4, 5, 6]
+    kw = dict(scale=1e-4, outer_iterlim=6, inner_iterlim=400)
+    batch = ScenarioBatch(case, ids, rho_pq=4e2, rho_va=4e4, tight_factor=0.99, spread=0.05)
+    batch.solve(**kw)
+    cumuls = []
+    for k, s in enumerate(ids):
+        env = AdmmEnv(case, 4e2, 4e4, use_gpu=True, verbose=0, tight_factor=0.99)
+        mod = ModelAcopf(env)
+        Pd, Qd = scenario_loads(mod.grid_data, s, spread=0.05)
+        mod.set_load(Pd, Qd)
+        env.params.scale, env.params.outer_iterlim, env.params.inner_iterlim = kw["scale"], kw["outer_iterlim"], kw["inner_iterlim"]
+        admm_two_level(env, mod, None, mode="native")
+        b = batch.models[k]
+        assert (b.info.status, b.info.outer, b.info.cumul) == (mod.info.status, mod.info.outer, mod.info.cumul), (s, vars(b.info))
+        assert b.info.objval == mod.info.objval
+        for name in ("u_curr", "v_curr", "z_curr", "l_curr", "lz", "rp", "rd"):
+            np.testing.assert_array_equal(getattr(b.solution, name), getattr(mod.solution, name), err_msg=f"scenario {s} {name}")
+        np.testing.assert_array_equal(b.membuf[24:27], mod.membuf[24:27])
+        cumuls.append(mod.info.cumul)
+        if k < 2:                                    # and the oracle on the same loads
+            par = Parameters(); par.verbose = 0; par.scale = kw["scale"]
+            par.outer_iterlim, par.inner_iterlim = kw["outer_iterlim"], kw["inner_iterlim"]
+            om = OracleModel(mod.grid_data, par, 4e2, 4e4)
+            om.set_load(Pd, Qd)
+            oi = om.admm_two_level()
+            assert (b.info.outer, b.info.cumul) == (oi.outer, oi.cumul)
+            assert abs(b.info.objval - oi.objval) <= 1e-6 * abs(oi.objval)
+        mod.close()
+    assert len(set(cumuls)) > 1                      # the scenarios really stop at different iterations
+    batch.close()
