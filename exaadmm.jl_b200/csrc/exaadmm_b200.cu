@@ -719,14 +719,14 @@ int ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_
     if (chunk <= 0) chunk = h->default_chunk;
     const double eps_pri = std::sqrt((double)h->nvar_global) / (2500.0 * (double)outer);    // admm_two_level.jl:45
     if (inner_limit == inner_start) { *inner_done = inner_start; for (int k = 0; k < 4; ++k) out[k] = 0.0; return EA_OK; }
-    CK(cudaEventRecord(h->span0, h->stream));
-    int rc = sync_ctrl_to_device(h, beta, eps_pri, inner_start, inner_limit);
-    if (rc) return rc;
+    int rc;
     int64_t enq = inner_start;
     // (partitioned handles too: the exchange is part of the chunk - peer stores inside the bus kernel, or the captured
     //  ncclAllGather; every rank replays the same graph, launches after `done` are no-ops on every rank alike)
     const bool graph = h->use_graph && !h->kernel_timing && !h->loopback && chunk > 1 && inner_limit - inner_start >= chunk;
-    if (graph && (rc = build_loop_graph(h, chunk, max_auglag, mu_max, scale))) return rc;
+    if (graph && (rc = build_loop_graph(h, chunk, max_auglag, mu_max, scale))) return rc;     // host work: before the span
+    CK(cudaEventRecord(h->span0, h->stream));
+    if ((rc = sync_ctrl_to_device(h, beta, eps_pri, inner_start, inner_limit))) return rc;
     for (;;) {
         const int64_t todo = graph ? chunk : std::min<int64_t>(chunk, inner_limit - enq);
         if (graph) {
