@@ -568,6 +568,169 @@ template <int N> EA_DEV void compute_step(double (&x)[N], const double (&xl)[N],
     snorm = nrm2<N>(s);
 }
 
+// Plain Cholesky of the masked matrix (fixed rows / columns replaced by the identity), no scaling, no shift search.
+// false if a pivot is not positive.
+template <int N> EA_DEV bool chol_masked(const Sym<N> &A, unsigned freemask, Chol<N> &L) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const bool fi = (freemask >> i) & 1u;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const bool fj = (freemask >> j) & 1u;
+            L.a[tri(i, j)] = (fi && fj) ? A.a[tri(i, j)] : ((i == j) ? 1.0 : 0.0);
+        }
+    }
+    return cholesky<N>(L);
+}
+
+// The common case of one dtron COMPUTE, taken in one go: a Newton step.
+//
+// 93 % of the calls of compute_step on this problem class run the same course: the Cauchy search ends on the straight
+// part of the projected path; no variable reaches a bound on the way; the Hessian restricted to the free variables is
+// positive definite, so the unshifted Cholesky factor is an exact preconditioner and the conjugate-gradient loop ends
+// after ONE step - the Newton correction w = -A_FF^-1 (A s_c + g)_F if it stays inside the trust region, otherwise the
+// same direction cut at the boundary -; the projected search takes the step without touching a bound; dspcg returns. newton_step computes exactly
+// that outcome directly - the Cauchy scalars, one Cholesky factorization, two triangular solves - and verifies every
+// condition the literal algorithm would have tested on the way (trust region in the preconditioned norm, bounds,
+// residual of the face after an interior step). If any of them fails it returns false WITHOUT touching its arguments and the caller runs the
+// literal algorithm (compute_step). Results agree with the literal path to rounding (the step is the same
+// vector computed with fewer operations), decisions except within rounding of a tie; EA_EXACT builds never take it.
+template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                         const Sym<N> &A, const double (&g)[N], double delta,
+                                         double &alphac, double &prered, double &gts, double &snorm, Stats &st) {
+#if EA_EXACT
+    return false;
+#else
+    const double mu0 = 0.01, interpf = 0.1, extrapf = 10.0, cgtol = 0.1;
+    // ---- Cauchy search in closed form on the straight part of the projected path: up to the first break point the
+    // projected step is s(alpha) = -alpha gh (gh = g on the variables that can move, 0 on those held by a bound), so
+    // |s| = alpha |gh|, g's = -alpha gh'gh, q(s) = alpha (alpha/2 gh'A gh - gh'gh): the trials of dcauchy are scalar ----
+    double gh[N], bp[N];
+    bool has[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double wi = -g[i];
+        const bool up = (x[i] < xu[i]) && (wi > 0.0);
+        const bool dn = (x[i] > xl[i]) && (wi < 0.0);
+        has[i] = up || dn;
+        bp[i] = ddiv((up ? xu[i] : xl[i]) - x[i], has[i] ? wi : 1.0);
+        gh[i] = has[i] ? g[i] : 0.0;
+    }
+    bool any = false;
+    double brptmin = 0.0, brptmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double lo = any ? dmin(brptmin, bp[i]) : bp[i];
+        const double hi = any ? dmax(brptmax, bp[i]) : bp[i];
+        brptmin = has[i] ? lo : brptmin;
+        brptmax = has[i] ? hi : brptmax;
+        any = any || has[i];
+    }
+    if (!any) return false;
+    double Ag[N];
+    symv<N>(A, gh, Ag);
+    const double gg = dot<N>(gh, gh), gAg = dot<N>(gh, Ag);
+    const double gnorm = dsqrt(gg);
+    double alpha = alphac, alphas = alphac;
+    int mode = 0;
+#pragma unroll 1
+    while (mode < 3) {
+        if (!(alpha < brptmin)) return false;                // leaves the straight part (or lands on a bound)
+        const bool within = alpha * gnorm <= delta;
+        const double tgts = -(alpha * gg);
+        const double q = alpha * EA_FMA(0.5 * alpha, gAg, -gg);
+        if (mode == 0) {
+            const bool interp = !within || (q >= mu0 * tgts);
+            if (interp) { mode = 1; alpha = interpf * alpha; }
+            else {
+                alphas = alpha;
+                if (alpha <= brptmax) { mode = 2; alpha = extrapf * alpha; }
+                else mode = 3;
+            }
+        } else if (mode == 1) {
+            if (within && !(q > mu0 * tgts)) mode = 4;
+            else alpha = interpf * alpha;
+        } else {
+            bool search = true;
+            if (within) { if (q < mu0 * tgts) alphas = alpha; }
+            else search = false;
+            if (search && alpha <= brptmax) alpha = extrapf * alpha;
+            else { alpha = alphas; mode = 3; }
+        }
+    }
+    if (!(alpha < brptmin)) return false;
+    // ---- the point after the Cauchy step and its free set (dspcg) ----
+    double sc[N], x1[N];
+    unsigned freemask = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        sc[i] = -alpha * gh[i];
+        x1[i] = dmax(xl[i], dmin(x[i] + sc[i], xu[i]));
+        if (xl[i] < x1[i] && x1[i] < xu[i]) freemask |= (1u << i);
+    }
+    if (freemask == 0) return false;
+    Chol<N> L;
+    if (!chol_masked<N>(A, freemask, L)) return false;       // not positive definite: the shift search of dicfs decides
+    // ---- Newton correction on the free variables: A_FF w = -(A s_c + g)_F ----
+    double gfree[N], w[N];
+    double gsq = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const bool fr = (freemask >> i) & 1u;
+        gfree[i] = fr ? EA_FMA(-alpha, Ag[i], g[i]) : 0.0;
+        const double gi = fr ? g[i] : 0.0;
+        gsq = EA_FMA(gi, gi, gsq);
+        w[i] = -gfree[i];
+    }
+    lsolve<N>(L, w);
+    const double pp = dot<N>(w, w);                           // |p|^2, p = L^-1 (-gfree): the first CG direction
+    if (!(pp > 0.0)) return false;                            // zero residual: dtrpcg's own exit
+    // dtrpcg, first iteration: with the exact factor p'(L^-1 A L^-T)p = p'p, so alpha = 1 and the step is p unless it
+    // leaves the trust region (alpha >= sigma = delta / |p|): then the step is sigma p and dspcg returns after this face
+    const double dsq = delta * delta;
+    const bool boundary = !(pp < dsq);
+    if (boundary) {
+        const double sigma = ddiv(dsqrt(pp * dsq), pp);       // dtrqsol with w = 0
+#pragma unroll
+        for (int i = 0; i < N; ++i) w[i] = sigma * w[i];
+    }
+    ltsolve<N>(L, w);
+    // the projected search must take the full step without reaching a bound (break points of w all >= 1)
+    double xt[N], s[N];
+    bool inside = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const bool fr = (freemask >> i) & 1u;
+        const double wi = fr ? w[i] : 0.0;
+        inside = inside && (wi > 0.0 ? (xu[i] - x1[i] >= wi) : (wi < 0.0 ? (xl[i] - x1[i] <= wi) : true));
+        w[i] = wi;
+        xt[i] = dmax(xl[i], dmin(x1[i] + wi, xu[i]));
+        s[i] = sc[i] + wi;
+    }
+    if (!inside) return false;
+    // the face is optimal: |(A s + g)_F| <= cgtol |g_F| (also the stopping test of the CG step itself)
+    double As[N];
+    symv<N>(A, s, As);
+    double gf2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double v = ((freemask >> i) & 1u) ? (As[i] + g[i]) : 0.0;
+        gf2 = EA_FMA(v, v, gf2);
+    }
+    // (after a boundary step dspcg returns whatever the residual is)
+    if (!boundary && !(gf2 <= (cgtol * cgtol) * gsq)) return false;
+    // ---- accept: outputs of compute_step ----
+    gts = dot<N>(g, s);
+    prered = -EA_FMA(0.5, dot<N>(s, As), gts);
+    snorm = nrm2<N>(s);
+    alphac = alpha;
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = xt[i];
+    st.cg += 1;
+    return true;
+#endif
+}
+
 // The "EVALUATE" part of dtron (B.0): trust-region update and acceptance.
 // Returns: 0 = rejected (task F), 1 = accepted (task GH), 2 = converged/warn.
 EA_DEV int judge_step(double f_trial, double fc, double g0, double snorm, double prered,
