@@ -475,18 +475,11 @@ EA_DEV void compute(Lane &L, const double (&xl)[N], const double (&xu)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) L.xc(i) = L.x[i];
     tron::Stats st;
-    // A branch that has needed EA_FAST_EVALS evaluations is on a long chain (a penalty ladder, or a trust-region-limited
-    // solve at a large penalty): its steps are (cut) Newton steps, which tron::newton_step takes directly - 93 % success,
-    // 30 % less time per step on a lone lane. Branches below the threshold take the literal algorithm alone: they run in
-    // full warps, where a failed attempt of one lane costs every lane the time of both paths; by the time a lane
-    // qualifies, the branch queue is nearly drained and warps hold a few live lanes each. The rule depends on the
-    // branch's own history only, so a branch gives the same bits wherever and whenever it is solved.
-#ifndef EA_FAST_EVALS
-#define EA_FAST_EVALS 2
-#endif
-    if (!(EA_FAST_EVALS > 0 && L.evals >= EA_FAST_EVALS &&
-          tron::newton_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st)))
-        tron::compute_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st);
+    // From its second evaluation on (EA_FAST_EVALS) a branch's steps are, 93 % of the time, Newton steps - interior or cut
+    // at the trust-region boundary -, which tron::newton_step takes directly: 30-35 % less time per step on a lone lane,
+    // the regime of the kernel's tail. The very first step of a branch takes the literal algorithm alone. The rule depends
+    // on the branch's own history only, so a branch gives the same bits wherever and whenever it is solved.
+    tron::compute_step_auto<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st, L.evals);
     L.cg += st.cg;
     L.shifts += st.shifts;
     L.phase = TRIAL;

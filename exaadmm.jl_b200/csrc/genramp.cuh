@@ -77,7 +77,7 @@ EA_DEV void tron_solve(const Problem &P, double mu, double xi, double (&x)[N], c
             for (int i = 0; i < N; ++i) xc[i] = x[i];
             double prered, g0, snorm;
             tron::Stats st;
-            tron::compute_step<N>(x, xl, xu, A, g, delta, alphac, prered, g0, snorm, st);
+            tron::compute_step_auto<N>(x, xl, xu, A, g, delta, alphac, prered, g0, snorm, st, evals);
             cg += st.cg;
             const double fn = eval_f(P, mu, xi, x);
             nfev++; evals++;

@@ -179,7 +179,7 @@ EA_DEV void tron_solve(const Qp &P, double (&x)[N], const double (&xl)[N], const
             for (int i = 0; i < N; ++i) xc[i] = x[i];
             double prered, g0, snorm;
             tron::Stats st;
-            tron::compute_step<N>(x, xl, xu, P.A, g, delta, alphac, prered, g0, snorm, st);
+            tron::compute_step_auto<N>(x, xl, xu, P.A, g, delta, alphac, prered, g0, snorm, st, evals);
             cg += st.cg;
             double fn;
             eval_fg(P, x, fn, gn);

@@ -731,6 +731,20 @@ template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], 
 #endif
 }
 
+// compute_step, with the direct (cut) Newton step tried first when `try_fast` (callers pass "this problem has needed at
+// least EA_FAST_EVALS evaluations": a rule that depends on the problem's own history only).
+#ifndef EA_FAST_EVALS
+#define EA_FAST_EVALS 2
+#endif
+template <int N> EA_DEV void compute_step_auto(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                               const Sym<N> &A, const double (&g)[N], double delta,
+                                               double &alphac, double &prered, double &gts, double &snorm,
+                                               Stats &st, int evals_so_far) {
+    if (EA_FAST_EVALS > 0 && evals_so_far >= EA_FAST_EVALS &&
+        newton_step<N>(x, xl, xu, A, g, delta, alphac, prered, gts, snorm, st)) return;
+    compute_step<N>(x, xl, xu, A, g, delta, alphac, prered, gts, snorm, st);
+}
+
 // The "EVALUATE" part of dtron (B.0): trust-region update and acceptance.
 // Returns: 0 = rejected (task F), 1 = accepted (task GH), 2 = converged/warn.
 EA_DEV int judge_step(double f_trial, double fc, double g0, double snorm, double prered,
