@@ -26,6 +26,21 @@
 #pragma once
 #include "tron.cuh"
 
+#ifdef EA_CYC
+__host__ __device__ __forceinline__ long long ea_clock() {
+#ifdef __CUDA_ARCH__
+    return clock64();
+#else
+    return 0;
+#endif
+}
+#define EA_CYC_T(t) const long long t = ea_clock()
+#define EA_CYC_ADD(L, k, a, b) (L).cyc[k] += (b) - (a)
+#else
+#define EA_CYC_T(t)
+#define EA_CYC_ADD(L, k, a, b)
+#endif
+
 namespace branch {
 
 constexpr int N = 6;
@@ -68,13 +83,15 @@ __host__ __device__ __noinline__ inline void mu_powers_general(double mu, double
     *inv_p01 = 1.0 / pow(mu, 0.1);          // only if mu was set from outside to something off the 10^k ladder
     *p09 = pow(mu, 0.9);
 }
-EA_DEV void mu_powers(const PowTable &T, double mu, double &inv_p01, double &p09) {
+// returns the index of mu in the table, -1 if it is not there
+EA_DEV int mu_powers(const PowTable &T, double mu, double &inv_p01, double &p09) {
 #pragma unroll 1
     for (int k = 0; k < T.n; ++k)
-        if (T.mu[k] == mu) { inv_p01 = T.inv_p01[k]; p09 = T.p09[k]; return; }
+        if (T.mu[k] == mu) { inv_p01 = T.inv_p01[k]; p09 = T.p09[k]; return k; }
     double a, b;
     mu_powers_general(mu, &a, &b);
     inv_p01 = a; p09 = b;
+    return -1;
 }
 
 #ifdef EA_PARITY
@@ -208,76 +225,57 @@ EA_DEV void eval_fgh_ref(const View &D, const double (&ls)[2], double mu, double
 }
 #endif
 
-// Fused f, grad f, Hessian (packed lower) of the scaled branch AL objective, and the four
-// flows F = (pij, qij, pji, qji) (acopf_eval_linelimit_kernel_gpu.jl:17-22).
+// f, grad f, Hessian (packed lower) of the scaled branch AL objective, and the four flows F = (pij, qij, pji, qji)
+// (acopf_eval_linelimit_kernel_gpu.jl:17-22), in three parts so that the driver can stop after the part it needs:
+//   eval_pre   what depends on the point only: sin / cos, the flows F_k = a_k vi^2 + b_k vj^2 + vi vj P_k(t), P_k and
+//              Q_k = dP_k/dt, the two line-limit constraint values;
+//   eval_fg    f and the gradient for given multipliers / penalty (ls, mu): the aggregated flow weights
+//              sum_k w_k (a, b, P, Q)_k, which the Hessian needs again, are handed on in Wsum;
+//   eval_hess  the Hessian.
+// A trial point whose TRON solve ends there needs f and g only (acceptance and convergence tests); and when the AL
+// update that follows keeps the point and changes (ls, mu), the START evaluation of the next solve is eval_fg + eval_hess
+// on the SAME Pre - bit for bit what a fresh evaluation at that point gives (same code, same inputs), without the
+// sincos and the flows. Flows 0, 1 are the from-side (b_k = 0), 2, 3 the to-side (a_k = 0): the zero terms are left out.
+struct Pre { double P[4], Q[4], F[4], c1, c2; };
+struct Wsum { double As, Bs, Ps, Qs, ri, rj; };
+
 template <class View>
-EA_DEV void eval_fgh(const View &D, const double (&ls)[2], double mu, double scale,
-                     const double (&x)[N], double &f, double (&g)[N], Sym6 &A, double (&F)[4]) {
-#ifdef EA_PARITY
-    eval_fgh_ref(D, ls, mu, scale, x, f, g, A);
-    {   // flows as the AL loop of the reference computes them (acopf_auglag_linelimit_kernel_gpu.jl:98-104, 135-138)
-        double sn, cs;
-        psincos(x[2] - x[3], &sn, &cs);
-        const double cc = x[0] * x[1] * cs, ss = x[0] * x[1] * sn;
-        F[0] = D.Y(0) * (x[0] * x[0]) + D.Y(2) * cc + D.Y(3) * ss;
-        F[1] = -D.Y(1) * (x[0] * x[0]) - D.Y(3) * cc + D.Y(2) * ss;
-        F[2] = D.Y(4) * (x[1] * x[1]) + D.Y(6) * cc - D.Y(7) * ss;
-        F[3] = -D.Y(5) * (x[1] * x[1]) - D.Y(7) * cc - D.Y(6) * ss;
-    }
-    return;
-#endif
+EA_DEV void eval_pre(const View &D, const double (&x)[N], Pre &p) {
     const double vi = x[0], vj = x[1];
     double s, c;
     sincos(x[2] - x[3], &s, &c);
     const double vv = vi * vj, vi2 = vi * vi, vj2 = vj * vj;
-    const double Y0 = D.Y(0), Y1 = D.Y(1), Y2 = D.Y(2), Y3 = D.Y(3), Y4 = D.Y(4), Y5 = D.Y(5), Y6 = D.Y(6), Y7 = D.Y(7);
-    // per-flow a, b, gamma, delta
-    const double a[4] = { Y0, -Y1, 0.0, 0.0 };
-    const double b[4] = { 0.0, 0.0, Y4, -Y5 };
+    const double Y2 = D.Y(2), Y3 = D.Y(3), Y6 = D.Y(6), Y7 = D.Y(7);
     const double ga[4] = { Y2, -Y3, Y6, -Y7 };
     const double de[4] = { Y3, Y2, -Y7, -Y6 };
-    double P[4], Q[4];
+    const double ab[4] = { D.Y(0), -D.Y(1), D.Y(4), -D.Y(5) };     // a_0, a_1, b_2, b_3
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        P[k] = ga[k] * c + de[k] * s;
-        Q[k] = de[k] * c - ga[k] * s;
-        F[k] = a[k] * vi2 + b[k] * vj2 + vv * P[k];
+        p.P[k] = ga[k] * c + de[k] * s;
+        p.Q[k] = de[k] * c - ga[k] * s;
+        p.F[k] = ab[k] * (k < 2 ? vi2 : vj2) + vv * p.P[k];
     }
-    const double c1 = F[0] * F[0] + F[1] * F[1] + x[4];
-    const double c2 = F[2] * F[2] + F[3] * F[3] + x[5];
-    const double m[2] = { ls[0] + mu * c1, ls[1] + mu * c2 };
+    p.c1 = p.F[0] * p.F[0] + p.F[1] * p.F[1] + x[4];
+    p.c2 = p.F[2] * p.F[2] + p.F[3] * p.F[3] + x[5];
+}
 
-    double fv = ls[0] * c1 + ls[1] * c2 + 0.5 * (mu * (c1 * c1)) + 0.5 * (mu * (c2 * c2));
-    // reduced (vi, vj, t) gradient / Hessian
+template <class View>
+EA_DEV void eval_fg(const View &D, const Pre &p, const double (&ls)[2], double mu, double scale,
+                    const double (&x)[N], double &f, double (&g)[N], Wsum &W) {
+    const double vi = x[0], vj = x[1];
+    const double vv = vi * vj, vi2 = vi * vi, vj2 = vj * vj;
+    const double ab[4] = { D.Y(0), -D.Y(1), D.Y(4), -D.Y(5) };
+    const double m[2] = { ls[0] + mu * p.c1, ls[1] + mu * p.c2 };
+    double fv = ls[0] * p.c1 + ls[1] * p.c2 + 0.5 * (mu * (p.c1 * p.c1)) + 0.5 * (mu * (p.c2 * p.c2));
     double As = 0.0, Bs = 0.0, Ps = 0.0, Qs = 0.0;        // sum_k w_k * (a,b,P,Q)_k
-    double H00 = 0.0, H01 = 0.0, H02 = 0.0, H11 = 0.0, H12 = 0.0, H22 = 0.0;
-    double d[2][3] = { { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 } };
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int j = k >> 1;
         const double lam = D.lam(k), rho = D.rho(k);
-        const double dev = F[k] - D.xt(k);
-        fv += lam * F[k] + 0.5 * (rho * (dev * dev));
-        const double G0 = 2.0 * a[k] * vi + vj * P[k];
-        const double G1 = 2.0 * b[k] * vj + vi * P[k];
-        const double G2 = vv * Q[k];
-        const double r = lam + rho * dev;
-        const double w = r + 2.0 * m[j] * F[k];
-        const double kap = rho + 2.0 * m[j];
-        As += w * a[k]; Bs += w * b[k]; Ps += w * P[k]; Qs += w * Q[k];
-        const double tF = 2.0 * F[k];
-        d[j][0] += tF * G0; d[j][1] += tF * G1; d[j][2] += tF * G2;
-        const double k0 = kap * G0, k1 = kap * G1, k2 = kap * G2;
-        H00 += k0 * G0; H01 += k0 * G1; H02 += k0 * G2;
-        H11 += k1 * G1; H12 += k1 * G2; H22 += k2 * G2;
-    }
-    H00 += 2.0 * As; H11 += 2.0 * Bs; H01 += Ps;
-    H02 += vj * Qs;  H12 += vi * Qs;  H22 -= vv * Ps;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const double m0 = mu * d[j][0], m1 = mu * d[j][1], m2 = mu * d[j][2];
-        H00 += m0 * d[j][0]; H01 += m0 * d[j][1]; H02 += m0 * d[j][2];
-        H11 += m1 * d[j][1]; H12 += m1 * d[j][2]; H22 += m2 * d[j][2];
+        const double dev = p.F[k] - D.xt(k);
+        fv += lam * p.F[k] + 0.5 * (rho * (dev * dev));
+        const double w = (lam + rho * dev) + 2.0 * m[k >> 1] * p.F[k];
+        if (k < 2) As += w * ab[k]; else Bs += w * ab[k];
+        Ps += w * p.P[k]; Qs += w * p.Q[k];
     }
     // consensus terms on w_i = vi^2, w_j = vj^2, t_i, t_j
     const double rho4 = D.rho(4), rho5 = D.rho(5), rho6 = D.rho(6), rho7 = D.rho(7);
@@ -288,18 +286,50 @@ EA_DEV void eval_fgh(const View &D, const double (&ls)[2], double mu, double sca
     f = scale * fv;
     const double ri = lam4 + rho4 * dwi;
     const double rj = lam5 + rho5 * dwj;
-    const double gy0 = 2.0 * As * vi + vj * Ps + 2.0 * vi * ri;
-    const double gy1 = 2.0 * Bs * vj + vi * Ps + 2.0 * vj * rj;
     const double gy2 = vv * Qs;
-    H00 += 2.0 * ri + 4.0 * rho4 * vi2;
-    H11 += 2.0 * rj + 4.0 * rho5 * vj2;
-
-    g[0] = scale * gy0;
-    g[1] = scale * gy1;
+    g[0] = scale * (2.0 * As * vi + vj * Ps + 2.0 * vi * ri);
+    g[1] = scale * (2.0 * Bs * vj + vi * Ps + 2.0 * vj * rj);
     g[2] = scale * (gy2 + lam6 + rho6 * dti);
     g[3] = scale * (-gy2 + lam7 + rho7 * dtj);
     g[4] = scale * m[0];
     g[5] = scale * m[1];
+    W.As = As; W.Bs = Bs; W.Ps = Ps; W.Qs = Qs; W.ri = ri; W.rj = rj;
+}
+
+template <class View>
+EA_DEV void eval_hess(const View &D, const Pre &p, const Wsum &W, const double (&ls)[2], double mu, double scale,
+                      const double (&x)[N], Sym6 &A) {
+    const double vi = x[0], vj = x[1];
+    const double vv = vi * vj, vi2 = vi * vi, vj2 = vj * vj;
+    const double ab[4] = { D.Y(0), -D.Y(1), D.Y(4), -D.Y(5) };
+    const double m[2] = { ls[0] + mu * p.c1, ls[1] + mu * p.c2 };
+    // reduced (vi, vj, t) Hessian
+    double H00 = 0.0, H01 = 0.0, H02 = 0.0, H11 = 0.0, H12 = 0.0, H22 = 0.0;
+    double d[2][3] = { { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 } };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int j = k >> 1;
+        const double G0 = (k < 2) ? 2.0 * ab[k] * vi + vj * p.P[k] : vj * p.P[k];
+        const double G1 = (k < 2) ? vi * p.P[k] : 2.0 * ab[k] * vj + vi * p.P[k];
+        const double G2 = vv * p.Q[k];
+        const double kap = D.rho(k) + 2.0 * m[j];
+        const double tF = 2.0 * p.F[k];
+        d[j][0] += tF * G0; d[j][1] += tF * G1; d[j][2] += tF * G2;
+        const double k0 = kap * G0, k1 = kap * G1, k2 = kap * G2;
+        H00 += k0 * G0; H01 += k0 * G1; H02 += k0 * G2;
+        H11 += k1 * G1; H12 += k1 * G2; H22 += k2 * G2;
+    }
+    H00 += 2.0 * W.As; H11 += 2.0 * W.Bs; H01 += W.Ps;
+    H02 += vj * W.Qs;  H12 += vi * W.Qs;  H22 -= vv * W.Ps;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const double m0 = mu * d[j][0], m1 = mu * d[j][1], m2 = mu * d[j][2];
+        H00 += m0 * d[j][0]; H01 += m0 * d[j][1]; H02 += m0 * d[j][2];
+        H11 += m1 * d[j][1]; H12 += m1 * d[j][2]; H22 += m2 * d[j][2];
+    }
+    const double rho4 = D.rho(4), rho5 = D.rho(5), rho6 = D.rho(6), rho7 = D.rho(7);
+    H00 += 2.0 * W.ri + 4.0 * rho4 * vi2;
+    H11 += 2.0 * W.rj + 4.0 * rho5 * vj2;
 
     using tron::tri;
     const double smu = scale * mu;
@@ -326,7 +356,35 @@ EA_DEV void eval_fgh(const View &D, const double (&ls)[2], double mu, double sca
     A.a[tri(5, 5)] = smu;
 }
 
-// The branch objective bound to a data view (what the kernel and the harness plug into Lane).
+// The whole evaluation at once (diagnostics, unit tests; the parity build's only form).
+template <class View>
+EA_DEV void eval_fgh(const View &D, const double (&ls)[2], double mu, double scale,
+                     const double (&x)[N], double &f, double (&g)[N], Sym6 &A, double (&F)[4]) {
+#ifdef EA_PARITY
+    eval_fgh_ref(D, ls, mu, scale, x, f, g, A);
+    {   // flows as the AL loop of the reference computes them (acopf_auglag_linelimit_kernel_gpu.jl:98-104, 135-138)
+        double sn, cs;
+        psincos(x[2] - x[3], &sn, &cs);
+        const double cc = x[0] * x[1] * cs, ss = x[0] * x[1] * sn;
+        F[0] = D.Y(0) * (x[0] * x[0]) + D.Y(2) * cc + D.Y(3) * ss;
+        F[1] = -D.Y(1) * (x[0] * x[0]) - D.Y(3) * cc + D.Y(2) * ss;
+        F[2] = D.Y(4) * (x[1] * x[1]) + D.Y(6) * cc - D.Y(7) * ss;
+        F[3] = -D.Y(5) * (x[1] * x[1]) - D.Y(7) * cc - D.Y(6) * ss;
+    }
+#else
+    Pre p;
+    Wsum W;
+    eval_pre(D, x, p);
+    eval_fg(D, p, ls, mu, scale, x, f, g, W);
+    eval_hess(D, p, W, ls, mu, scale, x, A);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) F[k] = p.F[k];
+#endif
+}
+
+// The branch objective bound to a data view (what the kernel and the harness plug into Lane). An evaluator that
+// declares the types Pre / Wsum and the three-part interface is driven part by part (eval_pass); one that only has
+// operator() (the parity build, the oracle's functions in the host harness) is called whole.
 template <class View> struct Objective {
     View D;
     double scale;
@@ -334,7 +392,18 @@ template <class View> struct Objective {
                            Sym6 &A, double (&F)[4]) const {
         eval_fgh(D, ls, mu, scale, x, f, g, A, F);
     }
+#ifndef EA_PARITY
+    using Pre = branch::Pre;
+    using Wsum = branch::Wsum;
+    EA_DEV void pre(const double (&x)[N], Pre &p) const { eval_pre(D, x, p); }
+    EA_DEV void fg(const Pre &p, const double (&x)[N], const double (&ls)[2], double mu, double &f, double (&g)[N],
+                   Wsum &W) const { eval_fg(D, p, ls, mu, scale, x, f, g, W); }
+    EA_DEV void hess(const Pre &p, const Wsum &W, const double (&x)[N], const double (&ls)[2], double mu,
+                     Sym6 &A) const { eval_hess(D, p, W, ls, mu, scale, x, A); }
+#endif
 };
+template <class E, class = void> struct is_split { static constexpr bool value = false; };
+template <class E> struct is_split<E, decltype((void)sizeof(typename E::Pre))> { static constexpr bool value = true; };
 
 enum Phase : int { NEED = 0, START = 1, RESTORE = 2, TRIAL = 3, DONE = 4 };
 
@@ -362,16 +431,20 @@ struct Lane {
     EA_DEV double &g0() const { return cold[(N + 10) * cs]; }
     EA_DEV double &snorm() const { return cold[(N + 11) * cs]; }
     int nfev, minor, iter, it_al;
+    int kmu;                                // index of mu in the PowTable (-1: off the ladder)
     int phase;
     bool step_pending;
     // work of the current branch
     int evals, cg, shifts, rejected, hit_max;
+#ifdef EA_CYC
+    long long cyc[8];                       // diagnostics build: SM cycles per section (tools/probe_branches.py)
+#endif
 };
 
 // Start a branch: x, ls, mu must be set by the caller (mu = 10 on the first inner
 // iteration of an outer iteration, acopf_auglag_linelimit_kernel_gpu.jl:75-80).
 EA_DEV void begin(Lane &L, const PowTable &T) {
-    mu_powers(T, L.mu, L.inv_p01(), L.p09());
+    L.kmu = mu_powers(T, L.mu, L.inv_p01(), L.p09());
     L.eta() = L.inv_p01();                       // eta = 1/mu^0.1 (:84)
     L.f() = L.fc() = L.delta = L.prered() = L.g0() = L.snorm() = 0.0;
     L.alphac = 1.0;
@@ -379,92 +452,153 @@ EA_DEV void begin(Lane &L, const PowTable &T) {
     L.phase = START;
     L.step_pending = false;
     L.evals = L.cg = L.shifts = L.rejected = L.hit_max = 0;
+#ifdef EA_CYC
+    for (int k = 0; k < 8; ++k) L.cyc[k] = 0;
+#endif
 #pragma unroll
     for (int i = 0; i < N; ++i) { L.g[i] = 0.0; L.xc(i) = L.x[i]; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) L.Fc(k) = 0.0;
 }
 
+// The evaluation in progress: the three-part form keeps Pre / Wsum between its parts, the whole form has nothing to keep.
+template <class Eval, bool SPLIT> struct EvalState;
+template <class Eval> struct EvalState<Eval, true> {
+    typename Eval::Pre p;
+    typename Eval::Wsum W;
+    EA_DEV void pre(const Eval &eval, const double (&x)[N]) { eval.pre(x, p); }
+    EA_DEV void fg(const Eval &eval, Lane &L, double &fn, double (&Fn)[4]) {
+        eval.fg(p, L.x, L.ls, L.mu, fn, L.g, W);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Fn[k] = p.F[k];
+    }
+    EA_DEV void hess(const Eval &eval, Lane &L) { eval.hess(p, W, L.x, L.ls, L.mu, L.A); }
+};
+template <class Eval> struct EvalState<Eval, false> {
+    EA_DEV void pre(const Eval &, const double (&)[N]) {}
+#pragma nv_exec_check_disable                        // (the host harness plugs host-only evaluators in)
+    EA_DEV void fg(const Eval &eval, Lane &L, double &fn, double (&Fn)[4]) { eval(L.x, L.ls, L.mu, fn, L.g, L.A, Fn); }
+    EA_DEV void hess(const Eval &, Lane &) {}
+};
+
+// mu moved one rung up the ladder: the powers of the next table entry, if mu is on the ladder (else the search).
+EA_DEV void mu_powers_next(const PowTable &T, Lane &L) {
+    const int k = L.kmu + 1;
+    if (L.kmu >= 0 && k < T.n && T.mu[k] == L.mu) { L.kmu = k; L.inv_p01() = T.inv_p01[k]; L.p09() = T.p09[k]; return; }
+    if (L.kmu >= 0 && T.mu[L.kmu] == L.mu) return;                 // mu_max reached: unchanged
+    L.kmu = mu_powers(T, L.mu, L.inv_p01(), L.p09());
+}
+
 // One evaluation phase. pass 0 serves lanes holding a trial point, pass 1 lanes at
 // the start of a TRON solve (or re-evaluating after a rejected step). Returns true
 // when the branch is finished (x, Fc, ls, mu hold the result).
+//
+// With a three-part evaluator (Objective in the fast build) a trial point is evaluated as far as its judgement needs
+// - f and g -; the Hessian follows only if the lane goes on from that point: the TRON solve continues, or the solve
+// ended, the AL update changed (ls, mu) and the next solve starts where this one stopped. In that last case the START
+// evaluation of the next solve is f, g, A for the new (ls, mu) on the flows already computed ("stage 1" below): same
+// values as a fresh evaluation, counted like one, without a second pass over the point.
 template <class Eval>
 EA_DEV bool eval_pass(Lane &L, const Eval &eval, int pass, const double (&xl)[N], const double (&xu)[N],
                       int max_auglag, double mu_max, const PowTable &T) {
     const int max_feval = 500, max_minor = 200;     // call site acopf_auglag_linelimit_kernel_gpu.jl:94
     const double gtol = 1e-6;
-    const bool mine = (pass == 0) ? (L.phase == TRIAL) : (L.phase == START || L.phase == RESTORE);
+    const bool mine = (pass == 0) ? (L.phase == TRIAL && !L.step_pending)
+                                  : ((L.phase == START || L.phase == RESTORE) && !L.step_pending);
     if (!mine) return false;
+    constexpr bool SPLIT = is_split<Eval>::value;
 
     double fn, Fn[4];
-    eval(L.x, L.ls, L.mu, fn, L.g, L.A, Fn);        // g, A always belong to the last evaluated point
-    if (L.phase != RESTORE) L.evals++;               // counted like the reference's f-evaluations
+    EvalState<Eval, SPLIT> es;
+    EA_CYC_T(c0);
+    es.pre(eval, L.x);
+    EA_CYC_T(c1);
+    EA_CYC_ADD(L, 0, c0, c1);
+    int stage = pass;                                // 0: judge the trial point, 1: start of a TRON solve
+#pragma unroll 1
+    for (;;) {
+        EA_CYC_T(c2);
+        es.fg(eval, L, fn, Fn);                      // g (and without the split A) belong to the last evaluated point
+        EA_CYC_T(c3);
+        EA_CYC_ADD(L, 1, c2, c3);
+        if (L.phase != RESTORE) L.evals++;           // counted like the reference's f-evaluations
 
-    if (pass == 1) {
-        L.f() = fn;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
-        if (L.phase == START) {                      // task 0: a fresh TRON solve
-            L.nfev = 1; L.minor = 1; L.iter = 1; L.alphac = 1.0;
-            L.delta = tron::nrm2<N>(L.g);            // tron_kernel.jl:102-105
-        }
-        L.step_pending = true;
-        return false;
-    }
-
-    bool tron_done = false;
-    L.nfev++;
-    if (L.nfev >= max_feval) {
-        tron_done = true;                            // driver stops, trial point kept (tron_kernel.jl:72-75)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
-    } else {
-        bool accepted;
-        const int task = tron::judge_step(fn, L.fc(), L.g0(), L.snorm(), L.prered(), L.iter == 1, L.delta, accepted);
-        if (accepted) {
-            L.iter++;
+        if (stage == 1) {
             L.f() = fn;
 #pragma unroll
             for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
-            if (task == 2) tron_done = true;
+            if (L.phase == START) {                  // task 0: a fresh TRON solve
+                L.nfev = 1; L.minor = 1; L.iter = 1; L.alphac = 1.0;
+                L.delta = tron::nrm2<N>(L.g);        // tron_kernel.jl:102-105
+            }
+            L.step_pending = true;
+            break;
+        }
+
+        bool tron_done = false, at_trial = true;     // at_trial: x is still the point just evaluated
+        L.nfev++;
+        if (L.nfev >= max_feval) {
+            tron_done = true;                        // driver stops, trial point kept (tron_kernel.jl:72-75)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
+        } else {
+            bool accepted;
+            const int task = tron::judge_step(fn, L.fc(), L.g0(), L.snorm(), L.prered(), L.iter == 1, L.delta, accepted);
+            if (accepted) {
+                L.iter++;
+                L.f() = fn;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) L.Fc(k) = Fn[k];
+                if (task == 2) tron_done = true;
+                else {
+                    L.minor++;                        // the reference evaluates g,H here (task GH)
+                    if (tron::gpnorm<N>(L.x, xl, xu, L.g) <= gtol) tron_done = true;          // NEWX test (:121-130)
+                    else if (L.minor >= max_minor) tron_done = true;
+                    else L.step_pending = true;
+                }
+            } else {
+                L.rejected++;
+                at_trial = false;
+#pragma unroll
+                for (int i = 0; i < N; ++i) L.x[i] = L.xc(i);
+                L.f() = L.fc();
+                if (task == 2) tron_done = true;      // Fc still holds the flows at xc
+                else L.phase = RESTORE;               // g, A must be re-evaluated at xc before the next step
+            }
+        }
+        if (!tron_done) {
+            if (L.step_pending) break;                // goes on from the trial point: needs its Hessian
+            return false;                             // rejected: pass 1 re-evaluates at xc
+        }
+
+        // augmented-Lagrangian update on the line limits (auglag_gpu.jl:96-131)
+        L.it_al++;
+        const double cviol1 = L.Fc(0) * L.Fc(0) + L.Fc(1) * L.Fc(1) + L.x[4];
+        const double cviol2 = L.Fc(2) * L.Fc(2) + L.Fc(3) * L.Fc(3) + L.x[5];
+        const double cnorm = tron::dmax(fabs(cviol1), fabs(cviol2));
+        bool terminate = false;
+        if (cnorm <= L.eta()) {
+            if (cnorm <= 1e-6) terminate = true;
             else {
-                L.minor++;                            // the reference evaluates g,H here (task GH)
-                if (tron::gpnorm<N>(L.x, xl, xu, L.g) <= gtol) tron_done = true;          // NEWX test (:121-130)
-                else if (L.minor >= max_minor) tron_done = true;
-                else L.step_pending = true;
+                L.ls[0] += L.mu * cviol1;
+                L.ls[1] += L.mu * cviol2;
+                L.eta() = L.eta() / L.p09();
             }
         } else {
-            L.rejected++;
-#pragma unroll
-            for (int i = 0; i < N; ++i) L.x[i] = L.xc(i);
-            L.f() = L.fc();
-            if (task == 2) tron_done = true;          // Fc still holds the flows at xc
-            else L.phase = RESTORE;                   // g, A must be re-evaluated at xc before the next step
+            L.mu = tron::dmin(mu_max, L.mu * 10.0);
+            mu_powers_next(T, L);
+            L.eta() = L.inv_p01();
         }
+        if (L.it_al >= max_auglag) { if (!terminate) L.hit_max = 1; terminate = true; }
+        if (terminate) { L.phase = DONE; return true; }
+        L.phase = START;
+        if (!SPLIT || !at_trial) return false;        // pass 1 evaluates at x
+        stage = 1;                                    // same point, new (ls, mu): f, g again, then the Hessian
     }
-    if (!tron_done) return false;
-
-    // augmented-Lagrangian update on the line limits (auglag_gpu.jl:96-131)
-    L.it_al++;
-    const double cviol1 = L.Fc(0) * L.Fc(0) + L.Fc(1) * L.Fc(1) + L.x[4];
-    const double cviol2 = L.Fc(2) * L.Fc(2) + L.Fc(3) * L.Fc(3) + L.x[5];
-    const double cnorm = tron::dmax(fabs(cviol1), fabs(cviol2));
-    bool terminate = false;
-    if (cnorm <= L.eta()) {
-        if (cnorm <= 1e-6) terminate = true;
-        else {
-            L.ls[0] += L.mu * cviol1;
-            L.ls[1] += L.mu * cviol2;
-            L.eta() = L.eta() / L.p09();
-        }
-    } else {
-        L.mu = tron::dmin(mu_max, L.mu * 10.0);
-        mu_powers(T, L.mu, L.inv_p01(), L.p09());
-        L.eta() = L.inv_p01();
-    }
-    if (L.it_al >= max_auglag) { if (!terminate) L.hit_max = 1; terminate = true; }
-    if (terminate) { L.phase = DONE; return true; }
-    L.phase = START;
+    EA_CYC_T(c4);
+    es.hess(eval, L);
+    EA_CYC_T(c5);
+    EA_CYC_ADD(L, 2, c4, c5);
     return false;
 }
 
@@ -475,11 +609,26 @@ EA_DEV void compute(Lane &L, const double (&xl)[N], const double (&xu)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) L.xc(i) = L.x[i];
     tron::Stats st;
-    // From its second evaluation on (EA_FAST_EVALS) a branch's steps are, 93 % of the time, Newton steps - interior or cut
-    // at the trust-region boundary -, which tron::newton_step takes directly: 30-35 % less time per step on a lone lane,
-    // the regime of the kernel's tail. The very first step of a branch takes the literal algorithm alone. The rule depends
-    // on the branch's own history only, so a branch gives the same bits wherever and whenever it is solved.
+    // tron::compute_step_auto: the step is taken directly where dtron's COMPUTE runs its common course (tron::newton_step:
+    // > 99.9 % of the steps of a solve of the BASELINE grids, tools/step_stats.py), by the literal algorithm otherwise.
+    // Which of the two runs depends on the branch's own data only, so a branch gives the same bits wherever and whenever
+    // it is solved.
+#ifdef EA_CYC
+    {
+        const long long t0 = ea_clock();
+        const bool ok = EA_FAST_EVALS > 0 && L.evals >= EA_FAST_EVALS &&
+                        tron::newton_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st);
+        const long long t1 = ea_clock();
+        if (ok) { L.cyc[4] += t1 - t0; L.cyc[7] += 1; }
+        else {
+            L.cyc[5] += t1 - t0;
+            tron::compute_step<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st);
+            L.cyc[6] += ea_clock() - t1;
+        }
+    }
+#else
     tron::compute_step_auto<N>(L.x, xl, xu, L.A, L.g, L.delta, L.alphac, L.prered(), L.g0(), L.snorm(), st, L.evals);
+#endif
     L.cg += st.cg;
     L.shifts += st.shifts;
     L.phase = TRIAL;

@@ -1182,6 +1182,9 @@ int ea_diag_branch_solve(int device, int per_warp, int64_t n, const double *prob
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; ++rep) {           // the second run is the timed one (instruction cache, clocks)
+#ifdef EA_CYC
+        { long long z[16] = { 0 }; CK(cudaMemcpyToSymbol(g_cyc, z, sizeof(z))); }
+#endif
         CK(cudaEventRecord(e0));
         k_diag_solve<<<nblocks(n * stride, XBLOCK), XBLOCK, XTILE_BYTES>>>((int)n, stride, dp, tmp.pow_table, max_auglag, mu_max,
                                                                           scale, ds, dw, dc);
@@ -1191,6 +1194,16 @@ int ea_diag_branch_solve(int device, int per_warp, int64_t n, const double *prob
     CK(cudaGetLastError());
     float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
     if (kernel_ms) *kernel_ms = ms;
+#ifdef EA_CYC
+    {   // section cycles of the long chains (>= 15 AL iterations), per AL iteration
+        long long c[16]; CK(cudaMemcpyFromSymbol(c, g_cyc, sizeof(c)));
+        const double al = (double)std::max(c[8], 1ll);
+        fprintf(stderr, "[cyc] %lld chains, %lld AL iterations, %.2f evals/AL; per AL iteration: total %.0f | pre %.0f fg %.0f hess %.0f | "
+                "newton ok %.0f (%.2f calls) newton failed %.0f literal %.0f | rest %.0f\n", c[11], c[8], c[10] / al, c[9] / al,
+                c[0] / al, c[1] / al, c[2] / al, c[4] / al, c[7] / al, c[5] / al, c[6] / al,
+                (c[9] - c[0] - c[1] - c[2] - c[4] - c[5] - c[6]) / al);
+    }
+#endif
     CK(cudaMemcpy(sol, ds, 13 * n * sizeof(double), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(work, dw, 6 * n * sizeof(int), cudaMemcpyDeviceToHost));
     static_assert(sizeof(long long) == sizeof(int64_t), "cycle counters are 64-bit");

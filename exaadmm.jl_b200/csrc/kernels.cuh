@@ -849,6 +849,9 @@ __global__ void k_diag_eval(int n, const double *x, const double *param, const d
 // prob: n x 56 (tests/golden/hard_branches.npz: lam8 rho8 xt8 Y8 | xl6 xu6 | x0(6) | ls0 ls1 mu | major rateA pad),
 // sol: n x 13 (x6 F4 ls0 ls1 mu), work: n x 6, cyc: n (SM cycles of the solve).
 // `stride` = 1: one problem per lane, 32: one per warp (a lone lane: the regime of the kernel's tail).
+#ifdef EA_CYC
+__device__ long long g_cyc[16];
+#endif
 __global__ void __launch_bounds__(XBLOCK, EA_XMINB)
 k_diag_solve(int n, int stride, const double *prob, branch::PowTable T, int max_auglag, double mu_max,
              double scale, double *sol, int *work, long long *cyc) {
@@ -898,6 +901,15 @@ k_diag_solve(int n, int stride, const double *prob, branch::PowTable T, int max_
 #pragma unroll
     for (int k = 0; k < 6; ++k) work[6 * (size_t)i + k] = w[k];
     cyc[i] = t1 - t0;
+#ifdef EA_CYC
+    if (L.it_al >= 15) {
+        for (int k = 0; k < 8; ++k) atomicAdd((unsigned long long *)&g_cyc[k], (unsigned long long)L.cyc[k]);
+        atomicAdd((unsigned long long *)&g_cyc[8], (unsigned long long)L.it_al);
+        atomicAdd((unsigned long long *)&g_cyc[9], (unsigned long long)(t1 - t0));
+        atomicAdd((unsigned long long *)&g_cyc[10], (unsigned long long)L.evals);
+        atomicAdd((unsigned long long *)&g_cyc[11], 1ull);
+    }
+#endif
 }
 
 // FP64 FMA peak probe: 8 independent DFMA chains per thread (roofline denominator of the

@@ -46,6 +46,17 @@
 
 namespace tron {
 
+// EA_STATS (host analysis build only, tools/step_stats.py): why newton_step declines, counted per reason.
+#ifdef EA_STATS
+static long long g_stat[2][16];
+static int g_stat_first = 0;
+#endif
+#if defined(EA_STATS) && !defined(__CUDA_ARCH__)
+#define EA_STAT(k) (tron::g_stat[tron::g_stat_first][k]++)
+#else
+#define EA_STAT(k) ((void)0)
+#endif
+
 // ---- scalar helpers ------------------------------------------------------------------
 // min / max without the NaN bookkeeping of fmin / fmax (inputs are finite)
 EA_DEV double dmin(double a, double b) { return a < b ? a : b; }
@@ -583,18 +594,26 @@ template <int N> EA_DEV bool chol_masked(const Sym<N> &A, unsigned freemask, Cho
     return cholesky<N>(L);
 }
 
-// The common case of one dtron COMPUTE, taken in one go: a Newton step.
+// One dtron COMPUTE taken directly, where it runs its common course.
 //
-// 93 % of the calls of compute_step on this problem class run the same course: the Cauchy search ends on the straight
-// part of the projected path; no variable reaches a bound on the way; the Hessian restricted to the free variables is
-// positive definite, so the unshifted Cholesky factor is an exact preconditioner and the conjugate-gradient loop ends
-// after ONE step - the Newton correction w = -A_FF^-1 (A s_c + g)_F if it stays inside the trust region, otherwise the
-// same direction cut at the boundary -; the projected search takes the step without touching a bound; dspcg returns. newton_step computes exactly
-// that outcome directly - the Cauchy scalars, one Cholesky factorization, two triangular solves - and verifies every
-// condition the literal algorithm would have tested on the way (trust region in the preconditioned norm, bounds,
-// residual of the face after an interior step). If any of them fails it returns false WITHOUT touching its arguments and the caller runs the
-// literal algorithm (compute_step). Results agree with the literal path to rounding (the step is the same
-// vector computed with fewer operations), decisions except within rounding of a tie; EA_EXACT builds never take it.
+// On this problem class the Hessian restricted to the free variables is positive definite on all but a handful of steps
+// per million, so the unshifted Cholesky factor is an EXACT preconditioner and the conjugate-gradient loop of a face
+// ends after ONE step - the Newton correction w = -A_FF^-1 (A s + g)_F if it stays inside the trust region, the same
+// direction cut at the boundary otherwise (info = 4). newton_step computes that course without the machinery around it:
+//   * the Cauchy search on scalars while the trial stays on the straight part of the projected path (up to the first
+//     break point s(alpha) = -alpha gh, so |s| = alpha |gh|, g's = -alpha gh'gh, q = alpha (alpha/2 gh'A gh - gh'gh):
+//     one matrix-vector product for the whole search); trials beyond the first break point as dcauchy evaluates them;
+//   * per face of dspcg one masked Cholesky factorization without scaling or shift search, two triangular solves, the
+//     trust-region cut; the projected search reduced to "the full step fits" where no break point of w lies below 1
+//     (then dprsrch does nothing else), dprsrch itself otherwise; dspcg's own exits (face optimal, boundary step, next
+//     face after a clipped step, at most three faces).
+// Every condition the literal algorithm would have tested on the way is re-checked; if one fails (pivot <= 0, zero
+// residual, an unclipped step that leaves a residual - the CG loop would go on -, a fourth face) newton_step returns
+// false WITHOUT touching its arguments and the caller runs the literal algorithm (compute_step). It covers > 99.9 % of
+// the steps of a solve of the BASELINE grids (tools/step_stats.py), first steps of a branch included. Results agree
+// with the literal path to rounding (the same vectors computed with fewer operations), decisions except within rounding
+// of a tie (tests/test_device_code_on_host.py::test_direct_step_follows_the_literal_algorithm); EA_EXACT builds never
+// take it.
 template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
                                          const Sym<N> &A, const double (&g)[N], double delta,
                                          double &alphac, double &prered, double &gts, double &snorm, Stats &st) {
@@ -626,7 +645,7 @@ template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], 
         brptmax = has[i] ? hi : brptmax;
         any = any || has[i];
     }
-    if (!any) return false;
+    if (!any) { EA_STAT(0); return false; }
     double Ag[N];
     symv<N>(A, gh, Ag);
     const double gg = dot<N>(gh, gh), gAg = dot<N>(gh, Ag);
@@ -635,10 +654,19 @@ template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], 
     int mode = 0;
 #pragma unroll 1
     while (mode < 3) {
-        if (!(alpha < brptmin)) return false;                // leaves the straight part (or lands on a bound)
-        const bool within = alpha * gnorm <= delta;
-        const double tgts = -(alpha * gg);
-        const double q = alpha * EA_FMA(0.5 * alpha, gAg, -gg);
+        bool within;
+        double tgts, q;
+        if (alpha < brptmin) {                               // on the straight part: scalars
+            within = alpha * gnorm <= delta;
+            tgts = -(alpha * gg);
+            q = alpha * EA_FMA(0.5 * alpha, gAg, -gg);
+        } else {                                             // a trial beyond the first break point: as dcauchy does it
+            EA_STAT(1);
+            double sp[N];
+            gpstep<N>(x, xl, xu, -alpha, g, sp);
+            within = nrm2<N>(sp) <= delta;
+            quad<N>(A, g, sp, q, tgts);
+        }
         if (mode == 0) {
             const bool interp = !within || (q >= mu0 * tgts);
             if (interp) { mode = 1; alpha = interpf * alpha; }
@@ -658,88 +686,120 @@ template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], 
             else { alpha = alphas; mode = 3; }
         }
     }
-    if (!(alpha < brptmin)) return false;
-    // ---- the point after the Cauchy step and its free set (dspcg) ----
-    double sc[N], x1[N];
-    unsigned freemask = 0;
+    // ---- the Cauchy step s, A s and the point after it (dspcg) ----
+    double sv[N], As[N], x1[N];
+    if (alpha < brptmin) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        sc[i] = -alpha * gh[i];
-        x1[i] = dmax(xl[i], dmin(x[i] + sc[i], xu[i]));
-        if (xl[i] < x1[i] && x1[i] < xu[i]) freemask |= (1u << i);
+        for (int i = 0; i < N; ++i) { sv[i] = -alpha * gh[i]; As[i] = -alpha * Ag[i]; }
+    } else {                                                 // the Cauchy point lies beyond the first break point
+        EA_STAT(2);
+        gpstep<N>(x, xl, xu, -alpha, g, sv);
+        symv<N>(A, sv, As);
     }
-    if (freemask == 0) return false;
-    Chol<N> L;
-    if (!chol_masked<N>(A, freemask, L)) return false;       // not positive definite: the shift search of dicfs decides
-    // ---- Newton correction on the free variables: A_FF w = -(A s_c + g)_F ----
-    double gfree[N], w[N];
-    double gsq = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const bool fr = (freemask >> i) & 1u;
-        gfree[i] = fr ? EA_FMA(-alpha, Ag[i], g[i]) : 0.0;
-        const double gi = fr ? g[i] : 0.0;
-        gsq = EA_FMA(gi, gi, gsq);
-        w[i] = -gfree[i];
-    }
-    lsolve<N>(L, w);
-    const double pp = dot<N>(w, w);                           // |p|^2, p = L^-1 (-gfree): the first CG direction
-    if (!(pp > 0.0)) return false;                            // zero residual: dtrpcg's own exit
-    // dtrpcg, first iteration: with the exact factor p'(L^-1 A L^-T)p = p'p, so alpha = 1 and the step is p unless it
-    // leaves the trust region (alpha >= sigma = delta / |p|): then the step is sigma p and dspcg returns after this face
+    for (int i = 0; i < N; ++i) x1[i] = dmax(xl[i], dmin(x[i] + sv[i], xu[i]));
+    // ---- the faces of dspcg, each taken in one go: exact Cholesky factor of A on the free variables -> the conjugate
+    // gradient loop is ONE step, the Newton correction w = -A_FF^-1 (A s + g)_F, cut at the trust-region boundary if it
+    // leaves it; projected search with its first trial (alpha = 1): the full step, clipped where a variable reaches a
+    // bound, if it passes the decrease test. Then dspcg's own tests: face optimal -> done; boundary step -> done; a
+    // clipped step leaves a smaller face -> once more. Anything else (pivot <= 0, zero residual, decrease test failed,
+    // an unclipped interior step that leaves a residual, more than three faces) is left to the literal algorithm. ----
     const double dsq = delta * delta;
-    const bool boundary = !(pp < dsq);
-    if (boundary) {
-        const double sigma = ddiv(dsqrt(pp * dsq), pp);       // dtrqsol with w = 0
+    int ncg = 0;
+    bool done = false;
+#pragma unroll 1
+    for (int face = 0; face < 3; ++face) {
+        unsigned freemask = 0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) w[i] = sigma * w[i];
-    }
-    ltsolve<N>(L, w);
-    // the projected search must take the full step without reaching a bound (break points of w all >= 1)
-    double xt[N], s[N];
-    bool inside = true;
+        for (int i = 0; i < N; ++i)
+            if (xl[i] < x1[i] && x1[i] < xu[i]) freemask |= (1u << i);
+        if (freemask == 0) {
+            if (face == 0) { EA_STAT(3); return false; }
+            done = true;                                     // dspcg returns with the step it has
+            break;
+        }
+        Chol<N> L;
+        if (!chol_masked<N>(A, freemask, L)) { EA_STAT(4); return false; }   // not positive definite: dicfs decides
+        double gfree[N], w[N];
+        double gsq = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const bool fr = (freemask >> i) & 1u;
-        const double wi = fr ? w[i] : 0.0;
-        inside = inside && (wi > 0.0 ? (xu[i] - x1[i] >= wi) : (wi < 0.0 ? (xl[i] - x1[i] <= wi) : true));
-        w[i] = wi;
-        xt[i] = dmax(xl[i], dmin(x1[i] + wi, xu[i]));
-        s[i] = sc[i] + wi;
-    }
-    if (!inside) return false;
-    // the face is optimal: |(A s + g)_F| <= cgtol |g_F| (also the stopping test of the CG step itself)
-    double As[N];
-    symv<N>(A, s, As);
-    double gf2 = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const bool fr = (freemask >> i) & 1u;
+            gfree[i] = fr ? (As[i] + g[i]) : 0.0;
+            const double gi = fr ? g[i] : 0.0;
+            gsq = EA_FMA(gi, gi, gsq);
+            w[i] = -gfree[i];
+        }
+        lsolve<N>(L, w);
+        const double pp = dot<N>(w, w);                       // |p|^2, p = L^-1 (-gfree): the first CG direction
+        if (!(pp > 0.0)) { EA_STAT(5); return false; }       // zero residual: dtrpcg's own exit
+        // dtrpcg, first iteration: with the exact factor p'(L^-1 A L^-T)p = p'p, so alpha = 1 and the step is p unless
+        // it leaves the trust region (alpha >= sigma = delta / |p|): then the step is sigma p (info = 4)
+        const bool boundary = !(pp < dsq);
+        if (boundary) {
+            const double sigma = ddiv(dsqrt(pp * dsq), pp);   // dtrqsol with w = 0
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const double v = ((freemask >> i) & 1u) ? (As[i] + g[i]) : 0.0;
-        gf2 = EA_FMA(v, v, gf2);
+            for (int i = 0; i < N; ++i) w[i] = sigma * w[i];
+        }
+        ltsolve<N>(L, w);
+        // dprsrch: no break point of w below 1 -> the full step (what dprsrch does then, without its divisions);
+        // otherwise dprsrch itself
+        bool inside = true;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool fr = (freemask >> i) & 1u;
+            const double wi = fr ? w[i] : 0.0;
+            const bool ok = (wi > 0.0) ? (xu[i] - x1[i] >= wi) : ((wi < 0.0) ? (xl[i] - x1[i] <= wi) : true);
+            inside = inside & ok;
+            w[i] = wi;
+        }
+        if (inside) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) x1[i] = dmax(xl[i], dmin(x1[i] + w[i], xu[i]));
+        } else {
+            EA_STAT(6);
+            prsrch<N>(x1, xl, xu, A, gfree, w);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) sv[i] += w[i];
+        symv<N>(A, sv, As);
+        ncg++;
+        double gf2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double v = ((freemask >> i) & 1u) ? (As[i] + g[i]) : 0.0;
+            gf2 = EA_FMA(v, v, gf2);
+        }
+        if (gf2 <= (cgtol * cgtol) * gsq) { done = true; break; }     // the face is optimal
+        if (boundary) { done = true; break; }                          // dspcg returns after a boundary step
+        if (inside) { EA_STAT(7); return false; }                      // the CG loop would go on
     }
-    // (after a boundary step dspcg returns whatever the residual is)
-    if (!boundary && !(gf2 <= (cgtol * cgtol) * gsq)) return false;
+    if (!done) { EA_STAT(11); return false; }
     // ---- accept: outputs of compute_step ----
-    gts = dot<N>(g, s);
-    prered = -EA_FMA(0.5, dot<N>(s, As), gts);
-    snorm = nrm2<N>(s);
+    gts = dot<N>(g, sv);
+    prered = -EA_FMA(0.5, dot<N>(sv, As), gts);
+    snorm = nrm2<N>(sv);
     alphac = alpha;
 #pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = xt[i];
-    st.cg += 1;
+    for (int i = 0; i < N; ++i) x[i] = x1[i];
+    st.cg += ncg;
+    EA_STAT(ncg > 1 ? 9 : 8);
     return true;
 #endif
 }
 
-// compute_step, with the direct (cut) Newton step tried first when `try_fast` (callers pass "this problem has needed at
-// least EA_FAST_EVALS evaluations": a rule that depends on the problem's own history only).
+// compute_step, with the direct step tried first once the problem has needed EA_FAST_EVALS evaluations (1: on every step;
+// 0: never, the literal algorithm alone - tests). A rule on the problem's own history only.
 #ifndef EA_FAST_EVALS
-#define EA_FAST_EVALS 2
+#define EA_FAST_EVALS 1
 #endif
 template <int N> EA_DEV void compute_step_auto(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
                                                const Sym<N> &A, const double (&g)[N], double delta,
                                                double &alphac, double &prered, double &gts, double &snorm,
                                                Stats &st, int evals_so_far) {
+#if defined(EA_STATS) && !defined(__CUDA_ARCH__)
+    g_stat_first = (evals_so_far < 2) ? 1 : 0;        // [1]: the first step of a problem
+#endif
     if (EA_FAST_EVALS > 0 && evals_so_far >= EA_FAST_EVALS &&
         newton_step<N>(x, xl, xu, A, g, delta, alphac, prered, gts, snorm, st)) return;
     compute_step<N>(x, xl, xu, A, g, delta, alphac, prered, gts, snorm, st);

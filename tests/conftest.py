@@ -110,3 +110,9 @@ def branch_inputs(grid, u, v, z, l, rho, membuf, I):
     Y = np.array([grid.YffR[I], grid.YffI[I], grid.YftR[I], grid.YftI[I], grid.YttR[I], grid.YttI[I],
                   grid.YtfR[I], grid.YtfI[I]])
     return x, xl, xu, param, Y
+
+
+@pytest.fixture(scope="session")
+def host_harness_literal():
+    """FMA build with the direct step (tron::newton_step) switched off: the literal TRON algorithm on every step."""
+    return _load_harness("_build_host_harness_literal.so")

@@ -62,6 +62,13 @@ static void run(const Eval &eval, double *x, const double *xl, const double *xu,
 
 extern "C" {
 
+#ifdef EA_STATS
+// analysis build (tools/step_stats.py): outcome counters of tron::newton_step, [later steps | first step] x reason
+void hh_stats(long long *out, int reset) {
+    for (int f = 0; f < 2; ++f) for (int k = 0; k < 16; ++k) { out[16 * f + k] = tron::g_stat[f][k]; if (reset) tron::g_stat[f][k] = 0; }
+}
+#endif
+
 // param: 31 doubles (membuf column, 0-based rows); rows 24-26 (lambda_s, mu) updated in place.
 // x: 6 doubles in/out. Y: 8. xl/xu: 6. work[6]: auglag, evals, cg, shifts, rejected, hit_max.
 void hh_solve_branch(double *x, const double *xl, const double *xu, double *param, const double *Y,

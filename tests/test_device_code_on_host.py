@@ -156,6 +156,37 @@ def test_branch_solver_random_problems_fma_build(host_harness):
     assert same_path >= 0.95 * total, (same_path, total)
 
 
+def test_direct_step_follows_the_literal_algorithm(host_harness, host_harness_literal):
+    """tron::newton_step (Cauchy search in closed form, one exact Cholesky factor and one CG step per face, projected
+    search only where a variable reaches a bound) against the literal algorithm it short-cuts, on the hardest branches
+    of a real solve (tests/golden/hard_branches.npz: penalty ladders, trust-region-limited solves at mu = 1e8, Cholesky
+    shifts, rejected steps) plus ordinary ones: same AL iterations everywhere; the same evaluation and CG counts and the
+    same solution to 1e-6 on all but the few solves whose path is rounding-sensitive."""
+    from pathlib import Path
+    d = np.load(Path(__file__).resolve().parent / "golden" / "hard_branches.npz")
+    prob, meta = d["prob"], d["meta"]
+    n = prob.shape[0]
+    res = {}
+    for name, H in (("direct", host_harness), ("literal", host_harness_literal)):
+        xs = np.zeros((n, 10)); ws = np.zeros((n, 6), dtype=np.int64)
+        for i in range(n):
+            p = prob[i]
+            param = np.zeros(31); param[0:24] = p[0:24]; param[24:27] = p[50:53]
+            Y = p[24:32].copy(); xl = p[32:38].copy(); xu = p[38:44].copy(); x = p[44:50].copy()
+            F = np.zeros(4); work = (C.c_int * 6)()
+            # major = 2: mu comes from param[26] (the fixture stores the mu the solve started with)
+            H.hh_solve_branch(P(x), P(xl), P(xu), P(param), P(Y), 2, int(meta[2]), float(meta[1]), float(meta[0]), P(F), work)
+            xs[i, :6] = x; xs[i, 6:] = F; ws[i] = list(work)
+        res[name] = (xs, ws)
+    (xd, wd), (xl_, wl) = res["direct"], res["literal"]
+    assert wl[:, 1].max() >= 150 and (wl[:, 0] >= 20).sum() >= 50
+    np.testing.assert_array_equal(wd[:, 0], wl[:, 0])                         # AL iterations
+    same = (wd[:, 1] == wl[:, 1]) & (wd[:, 2] == wl[:, 2])                    # evaluations and CG iterations
+    assert same.mean() >= 0.97, same.mean()
+    np.testing.assert_allclose(xd[same], xl_[same], rtol=0, atol=1e-6)
+    assert np.abs(xd - xl_).max() <= 1e-4
+
+
 # ---------------------------------------------------------------------------
 # multi-period model: the n = 3 generator sub-problem (genramp.cuh) against the oracle
 # ---------------------------------------------------------------------------
