@@ -912,6 +912,16 @@ k_diag_solve(int n, int stride, const double *prob, branch::PowTable T, int max_
 #endif
 }
 
+// measurement: stream a buffer through the L2 (option "l2_flush_clean")
+__global__ void k_l2_read(const double4 *p, size_t n, double *sink) {
+    double s = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double4 v = p[i];
+        s += v.x + v.y + v.z + v.w;
+    }
+    if (s == 123.456) *sink = s;                 // never true (the buffer holds zeros): keeps the loads
+}
+
 // FP64 FMA peak probe: 8 independent DFMA chains per thread (roofline denominator of the
 // branch kernel; MEASURED_PEAKS.json only has HBM and bf16 numbers).
 __global__ void k_fp64_peak(double *out, int iters) {

@@ -737,7 +737,7 @@ template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], 
         // it leaves the trust region (alpha >= sigma = delta / |p|): then the step is sigma p (info = 4)
         const bool boundary = !(pp < dsq);
         if (boundary) {
-            const double sigma = ddiv(dsqrt(pp * dsq), pp);   // dtrqsol with w = 0
+            const double sigma = delta * drsqrt(pp);         // dtrqsol with w = 0: delta / |p|
 #pragma unroll
             for (int i = 0; i < N; ++i) w[i] = sigma * w[i];
         }

@@ -411,7 +411,9 @@ int  ea_reset_counters(ea_handle_t *h);
  * "kernel_timing" (0/1, bracket every kernel of the fused loop with CUDA events),
  * "use_graph" (0/1, default 1: ea_run_inner* replays the chunk of iterations from a CUDA graph),
  * "l2_flush_mb" (measurement: with kernel_timing, a write of this many MB precedes every iteration, outside the
- * event brackets, so that every timed kernel starts from a cold L2). */
+ * event brackets, so that every timed kernel starts from a cold L2),
+ * "l2_flush_clean" (0/1, measurement: the write is followed by a read of a second buffer of the same size, which
+ * leaves the L2 holding clean lines instead of dirty ones waiting for their write-back). */
 int  ea_set_option(ea_handle_t *h, const char *name, double value);
 /* Launch accounting since the last ea_reset_counters: out = { device seconds spent in
  * ea_run_inner* (events on the library's stream), x-update launches, their summed
