@@ -654,7 +654,7 @@ static int enqueue_iteration(ea_handle *h, int max_auglag, double mu_max, double
     }
     int rc = launch_x(h, 0, 0, max_auglag, mu_max, scale, 1, 1);
     if (rc) return rc;
-    if (e) CK(cudaEventRecord(e[1], h->stream));
+    if (e && h->kernel_timing == 1) CK(cudaEventRecord(e[1], h->stream));      // (2: the iteration as a whole)
     k_bus<true><<<nblocks((int64_t)h->d.n_bus_warps * 32, BBLOCK), BBLOCK, 0, h->stream>>>(h->d, -1, 0.0);
     CK(cudaGetLastError());
     h->n_bus++;
@@ -757,8 +757,10 @@ int ea_run_inner_from(ea_handle_t *h, int64_t outer, double beta, int64_t inner_
             const int64_t ran = std::min<int64_t>(todo, h->ctrl_host->inner - (enq - todo));
             h->n_timed += std::max<int64_t>(ran, 0);
             for (int64_t i = 0; i < ran; ++i) {
-                h->t_x += elapsed_s(h->kev[3 * i], h->kev[3 * i + 1]);
-                h->t_bus += elapsed_s(h->kev[3 * i + 1], h->kev[3 * i + 2]);
+                if (h->kernel_timing == 1) {
+                    h->t_x += elapsed_s(h->kev[3 * i], h->kev[3 * i + 1]);
+                    h->t_bus += elapsed_s(h->kev[3 * i + 1], h->kev[3 * i + 2]);
+                } else h->t_x += elapsed_s(h->kev[3 * i], h->kev[3 * i + 2]);       // both kernels, back to back
             }
         }
         if (h->ctrl_host->done || enq >= inner_limit) break;
@@ -969,7 +971,7 @@ int ea_set_option(ea_handle_t *h, const char *name, double value) {
     if (!h || !name) return EA_ERR_ARG;
     if (!strcmp(name, "count_work")) { h->d.count_work = (int)value; return EA_OK; }   // 2: also phase timestamps
     if (!strcmp(name, "chunk")) { h->default_chunk = std::max(1, (int)value); return EA_OK; }
-    if (!strcmp(name, "kernel_timing")) { h->kernel_timing = value != 0.0; return EA_OK; }
+    if (!strcmp(name, "kernel_timing")) { h->kernel_timing = (value == 2.0) ? 2 : (value != 0.0); return EA_OK; }
     if (!strcmp(name, "use_graph")) { h->use_graph = value != 0.0; return EA_OK; }
     if (!strcmp(name, "l2_flush_mb")) {             // > 0: with kernel_timing, write this many MB before every iteration
         CK(cudaSetDevice(h->device));

@@ -408,7 +408,8 @@ int  ea_get_counters(ea_handle_t *h, ea_counters_t *out);
 int  ea_reset_counters(ea_handle_t *h);
 /* Options: "count_work" (0/1, atomics for ea_counters_t in the branch kernel, default 1),
  * "chunk" (inner iterations enqueued per host poll in ea_run_inner*, default 16),
- * "kernel_timing" (0/1, bracket every kernel of the fused loop with CUDA events),
+ * "kernel_timing" (0/1/2: bracket every kernel of the fused loop with CUDA events; 2: every ITERATION - the summed
+ * duration is reported as the x-update's, the bus kernel's as 0),
  * "use_graph" (0/1, default 1: ea_run_inner* replays the chunk of iterations from a CUDA graph),
  * "l2_flush_mb" (measurement: with kernel_timing, a write of this many MB precedes every iteration, outside the
  * event brackets, so that every timed kernel starts from a cold L2),
