@@ -596,7 +596,8 @@ def run_ours(args, rank, world, local_rank):
     n_gh = evals - cnt["rejected_steps"]
     n_steps = max(evals - cnt["auglag_iters"], 0)
     flops_alg = 119.0 * evals + 1356.0 * n_gh + 522.0 * n_steps + 144.0 * cnt["cg_iters"]
-    flops_exec = 1645.0 * evals       # executed DFMA x 2 + DMUL + DADD per evaluation (ncu, profiles/r1_fp64_ops_per_launch.csv)
+    flops_exec = 828.0 * evals        # executed DFMA x 2 + DMUL + DADD per evaluation (ncu, profiles/r2_xupdate.txt: 232.5 MFLOP in a
+                                      # launch of 281 k evaluations; 1645 in round 1)
     avg_x = t_x / n_x if n_x else float("nan")
     avg_b = t_b / n_b if n_b else float("nan")
     roof = {   # dominant kernel of the step. An FP64-pipe kernel by its arithmetic (nothing here is a contraction; 568 B per
@@ -610,20 +611,22 @@ def run_ours(args, rank, world, local_rank):
         "algorithmic_flops": "119 nfev + 1356 ngev + 522 steps + 144 cg (SURVEY 8d; counters of this pass)",
         "executed_flops_per_launch": flops_exec / n_x if n_x else None,
         "frac_executed": (flops_exec / t_x / 1e12 / fp64_peak.value) if (t_x and fp64_peak.value) else None,
-        "traffic": 45.5e6, "traffic_source": "ncu dram__bytes_read+write per launch at the 1-GPU size (cold L2, as in the timed "
-                                            "pass), profiles/r1_fp64_ops_per_launch.csv",
+        "traffic": 44.7e6, "traffic_source": "ncu dram__bytes_read+write per launch at the 1-GPU size (cold L2, as in the timed "
+                                            "pass), profiles/r2_xupdate.txt",
         "avg_launch_us": 1e6 * avg_x, "share_of_step": t_x / (t_x + t_b) if (t_x + t_b) else None,
         "hbm": {"achieved": x_bytes / avg_x / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": x_bytes / avg_x / 1e9 / hbm_peak,
                 "algorithmic_bytes_per_launch": x_bytes, "peak_source": peak_src},
         "evaluations_per_launch": evals / n_x if n_x else None,
         "critical_path": {"max_evaluations_of_one_branch": cnt["max_evals_lane"],
                           "mean_evaluations_per_branch": evals / max(cnt["line_calls"], 1),
-                          "note": "launch time ~ evaluations of the slowest branch x ~5 us (one lane, serial; DESIGN.md section 6)"},
+                          "note": "launch time ~ work queue drained (35-45 us) + the rest of the slowest branch at ~2 us per evaluation "
+                                  "(one lane, serial: 4.4 us per augmented-Lagrangian iteration; DESIGN.md section 6b)"},
     }
     roof_bus = {"kernel": "k_bus<fused> (bus consensus + z + lambda + residual norms)", "bound": "hbm",
                 "achieved": bus_bytes / avg_b / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": bus_bytes / avg_b / 1e9 / hbm_peak, "traffic": 31.9e6,
-                "traffic_source": "ncu dram bytes per launch (cold cache; the 50 MB working set is L2-resident in the loop)",
+                "frac": bus_bytes / avg_b / 1e9 / hbm_peak, "traffic": 34.7e6,
+                "traffic_source": "ncu dram bytes per launch, profiles/r2_bus.txt (cold cache: reads; the 17 MB it writes stay in "
+                                  "the L2; in the loop the 50 MB working set is L2-resident)",
                 "algorithmic_bytes_per_launch": bus_bytes, "avg_launch_us": 1e6 * avg_b,
                 "peak_source": peak_src,
                 "share_of_step": t_b / (t_x + t_b) if (t_x + t_b) else None}
