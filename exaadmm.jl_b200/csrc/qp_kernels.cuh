@@ -22,7 +22,7 @@ struct QpCtrl {
     int done;                 // 1: converged or outer == outer_limit; later launches are no-ops
     int solved;
     unsigned ticket;
-    int pad;
+    int next_line;            // work queue head of k_qp_xupdate (reset for the next x-update by k_qp_tail / k_qp_ctrl_begin)
 };
 
 struct QpDev {                // per-line arrays are SoA: row k of line I at [k * nline + I]
@@ -74,14 +74,21 @@ __global__ void k_qp_init_solution(Dev d, QpDev q, double rho_pq, double rho_va)
     }
 }
 
-// admm_update_x: generator_kernel_two_level on the qpsub bounds / costs + auglag_linelimit_qpsub, one lane per branch.
+// admm_update_x: generator_kernel_two_level on the qpsub bounds / costs + auglag_linelimit_qpsub.
 //   major_arg > 0: info.inner supplied by the host (step-wise API)
 //   major_arg == 0: fused loop (info.inner is 1 in every iteration of admm_one_level: mu restarts at 10), exits at once
 //                   when the loop has finished, and also saves v_prev <- v for the dual residual.
+// Persistent grid, one LANE per branch at a time, as in k_xupdate: branches come from a work queue (ctrl->next_line), a
+// lane that finishes its branch takes the next one, and the AL / TRON loops are the state machine of qpsub.cuh - per
+// round every live lane takes one TRON step, so the lanes of a warp run the same instructions although their branches
+// need 1 ... 30 AL iterations. (Round 1: one lane ran one branch to completion inside nested loops, 4.4 of 32 lanes
+// active per instruction.) The per-branch constants (47 doubles) and the bounds sit in a shared-memory column per lane.
+constexpr int QTILE_ROWS = qpsub::S_ROWS + 8;                // + xl[2..5], xu[2..5]
+
 __global__ void __launch_bounds__(QBLOCK)
 k_qp_xupdate(Dev d, QpDev q, branch::PowTable T, long long major_arg, int zsel, int max_auglag, double mu_max, double scale,
              int do_gens, int do_lines) {
-    __shared__ double tile[qpsub::S_ROWS * QBLOCK];
+    __shared__ double tile[QTILE_ROWS * QBLOCK];
     const bool fused = major_arg == 0;
     if (fused && q.ctrl->done) return;
     const long long major = fused ? 1 : major_arg;
@@ -94,68 +101,111 @@ k_qp_xupdate(Dev d, QpDev q, branch::PowTable T, long long major_arg, int zsel, 
         }
     if (!do_lines) return;
     const int nl = d.nline;
-    unsigned long long work[3] = { 0, 0, 0 };
+    const unsigned full = 0xffffffffu;
+    unsigned work[3] = { 0, 0, 0 };
     int mx = 0;
     qpsub::TileStore<QBLOCK> st{ tile + threadIdx.x };
-    // A warp runs as long as its slowest lane (a branch with binding limits: tens of TRON solves) and pays for every
-    // path its lanes take; with fewer branches than resident lanes the branches are spread over all warps, a few lanes
-    // each (2869-like grid, 4582 branches: 4 lanes per warp on 1184 warps instead of 32 lanes on 144).
-    const int nwarps = gridDim.x * (QBLOCK / 32), lane = threadIdx.x & 31, gwarp = tid >> 5;
+    double *bnd = tile + qpsub::S_ROWS * QBLOCK + threadIdx.x;
+    // with fewer branches than resident lanes the branches are spread over all warps, a few lanes each (2869-like grid,
+    // 4582 branches: 4 lanes per warp on 1184 warps instead of 32 lanes on 144): a round costs a warp less the fewer
+    // different stages its lanes are in
+    const int nwarps = gridDim.x * (QBLOCK / 32), lane = threadIdx.x & 31;
     const int lanes_on = min(32, max(1, (nl + nwarps - 1) / nwarps));
-    if (lane >= lanes_on) return;
-    for (int I = gwarp * lanes_on + lane; I < nl; I += nwarps * lanes_on) {
-        qpsub::Inputs in;
-        const int sf = d.slot_from[I], sto = d.slot_to[I];
-        {
-            const double *vh = d.v + d.gpad, *zh = z + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
-            const d4 lf = ld4(lh, sf), lt = ld4(lh, sto), rf = ld4(rh, sf), rt = ld4(rh, sto);
-            const d4 vf = ld4(vh, sf), vt = ld4(vh, sto), zf = ld4(zh, sf), zt = ld4(zh, sto);
-            if (fused) { st4(q.v_prev + d.gpad, sf, vf); st4(q.v_prev + d.gpad, sto, vt); }
-            const double lam[8] = { lf.p, lf.q, lt.p, lt.q, lf.w, lt.w, lf.t, lt.t };
-            const double rho[8] = { rf.p, rf.q, rt.p, rt.q, rf.w, rt.w, rf.t, rt.t };
-            const double xt[8] = { vf.p - zf.p, vf.q - zf.q, vt.p - zt.p, vt.q - zt.q, vf.w - zf.w, vt.w - zt.w, vf.t - zf.t, vt.t - zt.t };
+    qpsub::Lane L;
+    L.phase = (lane < lanes_on) ? qpsub::NEED : qpsub::DONE;
+    int I = -1;
+#pragma unroll 1
+    for (;;) {
+        // refill: lanes without a branch take the next ones from the queue
+        const bool need = (L.phase == qpsub::NEED);
+        const unsigned m = __ballot_sync(full, need);
+        if (m) {
+            int base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(&q.ctrl->next_line, __popc(m));
+            base = __shfl_sync(full, base, __ffs(m) - 1);
+            if (need) {
+                I = base + __popc(m & ((1u << lane) - 1u));
+                if (I >= nl) L.phase = qpsub::DONE;
+                else {
+                    qpsub::Inputs in;
+                    const int sf = d.slot_from[I], sto = d.slot_to[I];
+                    {
+                        const double *vh = d.v + d.gpad, *zh = z + d.gpad, *lh = d.l + d.gpad, *rh = d.rho + d.gpad;
+                        const d4 lf = ld4(lh, sf), lt = ld4(lh, sto), rf = ld4(rh, sf), rt = ld4(rh, sto);
+                        const d4 vf = ld4(vh, sf), vt = ld4(vh, sto), zf = ld4(zh, sf), zt = ld4(zh, sto);
+                        if (fused) { st4(q.v_prev + d.gpad, sf, vf); st4(q.v_prev + d.gpad, sto, vt); }
+                        const double lam[8] = { lf.p, lf.q, lt.p, lt.q, lf.w, lt.w, lf.t, lt.t };
+                        const double rho[8] = { rf.p, rf.q, rt.p, rt.q, rf.w, rt.w, rf.t, rt.t };
+                        const double xt[8] = { vf.p - zf.p, vf.q - zf.q, vt.p - zt.p, vt.q - zt.q, vf.w - zf.w, vt.w - zt.w, vf.t - zf.t, vt.t - zt.t };
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { in.lam[k] = lam[k]; in.rho[k] = rho[k]; in.xt[k] = xt[k]; in.Y[k] = d.Y[k * nl + I]; }
+                        for (int k = 0; k < 8; ++k) { in.lam[k] = lam[k]; in.rho[k] = rho[k]; in.xt[k] = xt[k]; in.Y[k] = d.Y[k * nl + I]; }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 21; ++k) in.H[k] = q.Hs[k * nl + I];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        in.res[k] = q.res[k * nl + I];
+                        in.LH_1h[k] = q.lin[k * nl + I];
+                        in.LH_1i[k] = q.lin[(5 + k) * nl + I];
+                    }
+                    in.RH_1h = q.lin[4 * nl + I]; in.RH_1i = q.lin[9 * nl + I];
+                    in.LH_1j[0] = q.lin[10 * nl + I]; in.LH_1j[1] = q.lin[11 * nl + I]; in.RH_1j = q.lin[12 * nl + I];
+                    in.LH_1k[0] = q.lin[13 * nl + I]; in.LH_1k[1] = q.lin[14 * nl + I]; in.RH_1k = q.lin[15 * nl + I];
+                    double x0[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        x0[k] = q.sqp_line[(2 + k) * nl + I];
+                        bnd[k * QBLOCK] = q.lsus[(2 + k) * nl + I];
+                        bnd[(4 + k) * QBLOCK] = q.lsus[(8 + k) * nl + I];
+                    }
+                    const double mu = (major == 1) ? 10.0 : q.membuf[4 * nl + I];
+                    qpsub::begin(L, in, st, x0, q.membuf[2 * nl + I], q.membuf[3 * nl + I], mu, T);
+                }
+            }
         }
+        if (__all_sync(full, L.phase == qpsub::DONE)) break;
+        qpsub::start_pass(L, st, scale);
+        double xl[6], xu[6];
+        xl[0] = 0.0; xl[1] = 0.0; xu[0] = 200000.0; xu[1] = 200000.0;
 #pragma unroll
-        for (int k = 0; k < 21; ++k) in.H[k] = q.Hs[k * nl + I];
+        for (int k = 0; k < 4; ++k) { xl[2 + k] = bnd[k * QBLOCK]; xu[2 + k] = bnd[(4 + k) * QBLOCK]; }
+        if (qpsub::step_pass(L, st, xl, xu, max_auglag, mu_max, T)) {
+            double Y[8], res[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            in.res[k] = q.res[k * nl + I];
-            in.LH_1h[k] = q.lin[k * nl + I];
-            in.LH_1i[k] = q.lin[(5 + k) * nl + I];
+            for (int k = 0; k < 8; ++k) Y[k] = d.Y[k * nl + I];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) res[k] = q.res[k * nl + I];
+            const double h2[2] = { q.lin[I], q.lin[nl + I] }, i2[2] = { q.lin[5 * nl + I], q.lin[6 * nl + I] };
+            qpsub::Result R;
+            qpsub::finish(L, st, Y, res, h2, i2, R);
+            const int sf = d.slot_from[I], sto = d.slot_to[I];
+            d4 of, ot;
+            of.p = R.u[0]; of.q = R.u[1]; of.w = R.u[4]; of.t = R.u[6];
+            ot.p = R.u[2]; ot.q = R.u[3]; ot.w = R.u[5]; ot.t = R.u[7];
+            st4(d.u + d.gpad, sf, of);
+            st4(d.u + d.gpad, sto, ot);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) q.sqp_line[k * nl + I] = R.sqp[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q.lambda[k * nl + I] = R.lambda[k];
+            q.membuf[2 * nl + I] = L.lam_j; q.membuf[3 * nl + I] = L.lam_k; q.membuf[4 * nl + I] = L.mu;
+            work[0] += 1; work[1] += (unsigned)R.it; work[2] += (unsigned)R.evals;
+            mx = max(mx, R.it);
+            L.phase = qpsub::NEED;
         }
-        in.RH_1h = q.lin[4 * nl + I]; in.RH_1i = q.lin[9 * nl + I];
-        in.LH_1j[0] = q.lin[10 * nl + I]; in.LH_1j[1] = q.lin[11 * nl + I]; in.RH_1j = q.lin[12 * nl + I];
-        in.LH_1k[0] = q.lin[13 * nl + I]; in.LH_1k[1] = q.lin[14 * nl + I]; in.RH_1k = q.lin[15 * nl + I];
-        double x0[4], xl[4], xu[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            x0[k] = q.sqp_line[(2 + k) * nl + I];
-            xl[k] = q.lsus[(2 + k) * nl + I];
-            xu[k] = q.lsus[(8 + k) * nl + I];
-        }
-        double lam_j = q.membuf[2 * nl + I], lam_k = q.membuf[3 * nl + I];
-        double mu = (major == 1) ? 10.0 : q.membuf[4 * nl + I];
-        qpsub::Result R;
-        qpsub::solve(in, st, x0, xl, xu, lam_j, lam_k, mu, max_auglag, mu_max, scale, T, R);
-        d4 of, ot;
-        of.p = R.u[0]; of.q = R.u[1]; of.w = R.u[4]; of.t = R.u[6];
-        ot.p = R.u[2]; ot.q = R.u[3]; ot.w = R.u[5]; ot.t = R.u[7];
-        st4(d.u + d.gpad, sf, of);
-        st4(d.u + d.gpad, sto, ot);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) q.sqp_line[k * nl + I] = R.sqp[k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) q.lambda[k * nl + I] = R.lambda[k];
-        q.membuf[2 * nl + I] = lam_j; q.membuf[3 * nl + I] = lam_k; q.membuf[4 * nl + I] = mu;
-        work[0] += 1; work[1] += (unsigned)R.it; work[2] += (unsigned)R.evals;
-        mx = max(mx, R.it);
     }
-    if (d.count_work && work[0]) {          // (lanes beyond lanes_on have left: no warp-wide shuffles here)
+    if (d.count_work) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) atomicAdd(&q.counters[k], work[k]);
-        atomicMax(&q.counters[3], (unsigned long long)mx);
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) work[k] += __shfl_down_sync(full, work[k], o);
+            mx = max(mx, __shfl_down_sync(full, mx, o));
+        }
+        if (lane == 0 && work[0]) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) atomicAdd(&q.counters[k], (unsigned long long)work[k]);
+            atomicMax(&q.counters[3], (unsigned long long)mx);
+        }
     }
 }
 
@@ -264,6 +314,7 @@ k_qp_tail(Dev d, QpDev q, int zsel, double beta, double *out) {
     block_sumK<8>(a, red);
     if (threadIdx.x == 0) {
         q.ctrl->ticket = 0u;
+        if (MODE == 1) q.ctrl->next_line = 0;
         const double objval = a[5] + a[6];
         // qpsub_admm_update_residual_gpu.jl:30-51; par.beta = 0 on the one-level path
         const double auglag = objval + a[4] + 0.5 * beta * a[7] + a[2] + 0.5 * a[3];
@@ -283,7 +334,7 @@ k_qp_tail(Dev d, QpDev q, int zsel, double beta, double *out) {
 
 __global__ void k_qp_ctrl_begin(QpCtrl *c, double outer_tol, double dual_tol, long long outer0, long long limit) {
     c->outer_tol = outer_tol; c->dual_tol = dual_tol; c->outer = outer0; c->outer_limit = limit;
-    c->done = (outer0 >= limit) ? 1 : 0; c->solved = 0; c->ticket = 0u;
+    c->done = (outer0 >= limit) ? 1 : 0; c->solved = 0; c->ticket = 0u; c->next_line = 0;
     for (int k = 0; k < 8; ++k) c->res[k] = 0.0;
 }
 

@@ -157,52 +157,6 @@ EA_DEV void eval_fg(const Qp &P, const double (&x)[N], double &f, double (&g)[N]
     for (int i = 0; i < N; ++i) g[i] = w[i] + P.b[i];
 }
 
-// tron_gpu_test (qpsub_tron_linelimit_kernel.jl:8-117) around ExaTron.dtron, one lane. g is the last gradient the
-// driver evaluated (`trg`: the reference reads it back for the multipliers).
-EA_DEV void tron_solve(const Qp &P, double (&x)[N], const double (&xl)[N], const double (&xu)[N], double (&g)[N],
-                       int &evals, int &cg) {
-    const int max_feval = 500, max_minor = 200;
-    const double gtol = 1e-6;
-    double f, gn[N];
-    eval_fg(P, x, f, g);
-    int nfev = 1, minor = 1, iter = 1;
-    evals++;
-    double delta = tron::nrm2<N>(g), alphac = 1.0;
-#pragma unroll 1
-    for (;;) {
-        int task;
-#pragma unroll 1
-        do {
-            const double fc = f;
-            double xc[N];
-#pragma unroll
-            for (int i = 0; i < N; ++i) xc[i] = x[i];
-            double prered, g0, snorm;
-            tron::Stats st;
-            tron::compute_step_auto<N>(x, xl, xu, P.A, g, delta, alphac, prered, g0, snorm, st, evals);
-            cg += st.cg;
-            double fn;
-            eval_fg(P, x, fn, gn);
-            nfev++; evals++;
-            if (nfev >= max_feval) return;
-            bool accepted;
-            task = tron::judge_step(fn, fc, g0, snorm, prered, iter == 1, delta, accepted);
-            if (accepted) { iter++; f = fn; }
-            else {
-#pragma unroll
-                for (int i = 0; i < N; ++i) x[i] = xc[i];
-                f = fc;
-            }
-        } while (task == 0);
-        if (task == 2) return;                       // converged on the function-value test: g stays the old gradient
-#pragma unroll
-        for (int i = 0; i < N; ++i) g[i] = gn[i];
-        minor++;
-        if (tron::gpnorm<N>(x, xl, xu, g) <= gtol) return;
-        if (minor >= max_minor) return;
-    }
-}
-
 struct Result {
     double u[8];            // pij, qij, pji, qji, wi, wj, ti, tj
     double sqp[6];          // w_ijR, w_ijI, w_i, w_j, theta_i, theta_j
@@ -210,44 +164,125 @@ struct Result {
     int it, evals, cg;
 };
 
-// The AL loop (auglag_linelimit_qpsub, ..red_gpu.jl:150-240). x0 = sqp_line[2..5] of the previous call; lam_j, lam_k, mu
-// are qpsub_membuf rows 3-5 (mu restarts at 10 when info.inner == 1: the caller passes it in).
+// The AL loop (auglag_linelimit_qpsub, ..red_gpu.jl:150-240) around tron_gpu_test (qpsub_tron_linelimit_kernel.jl:8-117,
+// ExaTron.dtron), flattened like the ACOPF branch solver (branch.cuh) into a state machine that the lanes of a warp, each
+// at a different stage of a different branch, advance in lock step:
+//     start_pass   lanes at the start of an AL iteration: the QP of this (lambda_j, lambda_k, mu), f and g at x
+//     step_pass    every live lane: one TRON step (dtron COMPUTE), f and g at the trial point, its judgement; when the
+//                  TRON solve ends, the AL update - the branch is finished or goes back to start_pass
+// The Hessian is constant within an AL iteration, so a rejected step needs no re-evaluation: the next round retries
+// with the smaller trust region. The kernel refills finished lanes from a work queue between the rounds; the host
+// harness drives the same functions for one branch (solve).
+enum Phase : int { NEED = 0, START = 1, RUN = 2, DONE = 3 };
+
+struct Lane {
+    double x[N], g[N];          // g: the last gradient the driver accepted (`trg`: read back for the multipliers)
+    Qp P;
+    double f, delta, alphac;
+    double lam_j, lam_k, mu;    // qpsub_membuf rows 3-5
+    double eta, inv_p01, p09;
+    int nfev, minor, iter, it, evals, cg;
+    int phase;
+};
+
+// x0 = sqp_line[2..5] of the previous call; mu restarts at 10 when info.inner == 1 (the caller passes it in).
 template <class Store>
-EA_DEV void solve(const Inputs &in, Store &st, const double (&x0)[4], const double (&xl4)[4], const double (&xu4)[4],
-                  double &lam_j, double &lam_k, double &mu, int max_auglag, double mu_max, double scale,
-                  const branch::PowTable &T, Result &R) {
+EA_DEV void begin(Lane &L, const Inputs &in, Store &st, const double (&x0)[4], double lam_j, double lam_k, double mu,
+                  const branch::PowTable &T) {
     setup(in, st);
-    double x[N] = { 0.0, 0.0, x0[0], x0[1], x0[2], x0[3] };
-    const double xl[N] = { 0.0, 0.0, xl4[0], xl4[1], xl4[2], xl4[3] };
-    const double xu[N] = { 200000.0, 200000.0, xu4[0], xu4[1], xu4[2], xu4[3] };
-    double trg[N] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
-    double inv_p01, p09;
-    branch::mu_powers(T, mu, inv_p01, p09);
-    double eta = inv_p01;
-    int it = 0;
-    bool terminate = false;
-    R.evals = 0; R.cg = 0;
-#pragma unroll 1
-    while (!terminate) {
-        it++;
-        Qp P;
-        build_qp(st, lam_j, lam_k, mu, scale, P);
-        tron_solve(P, x, xl, xu, trg, R.evals, R.cg);
-        double c3 = x[0] + st[S_DJ], c4 = x[1] + st[S_DK];
+    L.x[0] = 0.0; L.x[1] = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { c3 = EA_FMA(st[S_GJ + i], x[2 + i], c3); c4 = EA_FMA(st[S_GK + i], x[2 + i], c4); }
-        const double cnorm = tron::dmax(fabs(c3), fabs(c4));
-        if (cnorm <= eta) {
-            if (cnorm <= 1e-6) terminate = true;
-            else { lam_j += mu * c3; lam_k += mu * c4; eta = eta / p09; }
-        } else {
-            mu = tron::dmin(mu_max, mu * 10.0);
-            branch::mu_powers(T, mu, inv_p01, p09);
-            eta = inv_p01;
+    for (int i = 0; i < 4; ++i) L.x[2 + i] = x0[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) L.g[i] = 0.0;
+    L.lam_j = lam_j; L.lam_k = lam_k; L.mu = mu;
+    branch::mu_powers(T, mu, L.inv_p01, L.p09);
+    L.eta = L.inv_p01;
+    L.it = 0; L.evals = 0; L.cg = 0;
+    L.f = 0.0; L.delta = 0.0; L.alphac = 1.0; L.nfev = 0; L.minor = 0; L.iter = 1;
+    L.phase = START;
+}
+
+template <class Store>
+EA_DEV void start_pass(Lane &L, const Store &st, double scale) {
+    if (L.phase != START) return;
+    L.it++;
+    build_qp(st, L.lam_j, L.lam_k, L.mu, scale, L.P);
+    eval_fg(L.P, L.x, L.f, L.g);
+    L.nfev = 1; L.minor = 1; L.iter = 1;
+    L.evals++;
+    L.delta = tron::nrm2<N>(L.g);
+    L.alphac = 1.0;
+    L.phase = RUN;
+}
+
+// Returns true when the branch is finished (x, g, lam_j, lam_k, mu hold the result: finish()).
+template <class Store>
+EA_DEV bool step_pass(Lane &L, const Store &st, const double (&xl)[N], const double (&xu)[N], int max_auglag,
+                      double mu_max, const branch::PowTable &T) {
+    const int max_feval = 500, max_minor = 200;
+    const double gtol = 1e-6;
+    if (L.phase != RUN) return false;
+    const double fc = L.f;
+    double xc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) xc[i] = L.x[i];
+    double prered, g0, snorm;
+    tron::Stats s;
+    tron::compute_step_auto<N>(L.x, xl, xu, L.P.A, L.g, L.delta, L.alphac, prered, g0, snorm, s, L.evals);
+    L.cg += s.cg;
+    double fn, gn[N];
+    eval_fg(L.P, L.x, fn, gn);
+    L.nfev++; L.evals++;
+    bool tron_done = false;
+    if (L.nfev >= max_feval) tron_done = true;       // the driver stops with the trial point and the old gradient
+    else {
+        bool accepted;
+        const int task = tron::judge_step(fn, fc, g0, snorm, prered, L.iter == 1, L.delta, accepted);
+        if (accepted) { L.iter++; L.f = fn; }
+        else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) L.x[i] = xc[i];
+            L.f = fc;
         }
-        if (it >= max_auglag && cnorm > 1e-6) terminate = true;
+        if (task == 0) return false;                  // rejected: the next round retries with the smaller trust region
+        if (task == 2) tron_done = true;              // converged on the function-value test: g stays the old gradient
+        else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) L.g[i] = gn[i];
+            L.minor++;
+            if (tron::gpnorm<N>(L.x, xl, xu, L.g) <= gtol) tron_done = true;
+            else if (L.minor >= max_minor) tron_done = true;
+        }
     }
-    R.it = it;
+    if (!tron_done) return false;
+    // AL update on the two linearised line limits
+    double c3 = L.x[0] + st[S_DJ], c4 = L.x[1] + st[S_DK];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c3 = EA_FMA(st[S_GJ + i], L.x[2 + i], c3); c4 = EA_FMA(st[S_GK + i], L.x[2 + i], c4); }
+    const double cnorm = tron::dmax(fabs(c3), fabs(c4));
+    bool terminate = false;
+    if (cnorm <= L.eta) {
+        if (cnorm <= 1e-6) terminate = true;
+        else { L.lam_j += L.mu * c3; L.lam_k += L.mu * c4; L.eta = L.eta / L.p09; }
+    } else {
+        L.mu = tron::dmin(mu_max, L.mu * 10.0);
+        branch::mu_powers(T, L.mu, L.inv_p01, L.p09);
+        L.eta = L.inv_p01;
+    }
+    if (L.it >= max_auglag && cnorm > 1e-6) terminate = true;
+    if (terminate) { L.phase = DONE; return true; }
+    L.phase = START;
+    return false;
+}
+
+// What the branch hands back: u = supY (C x + d) + res, sqp_line, and the multipliers of 14h-14k (..red_gpu.jl:256-277).
+// Y, res and the leading 2 x 2 blocks of 1h / 1i are re-read by the caller (they are not kept during the solve).
+template <class Store>
+EA_DEV void finish(const Lane &L, const Store &st, const double (&Y)[8], const double (&res)[4], const double (&LH_1h)[2],
+                   const double (&LH_1i)[2], Result &R) {
+    const double (&x)[N] = L.x;
+    R.it = L.it; R.evals = L.evals; R.cg = L.cg;
     // x8 = C x + d
     double wR = st[S_DR], wI = st[S_DI];
 #pragma unroll
@@ -256,17 +291,18 @@ EA_DEV void solve(const Inputs &in, Store &st, const double (&x0)[4], const doub
 #pragma unroll
     for (int i = 0; i < 4; ++i) R.sqp[2 + i] = x[2 + i];
     double S[4][4];
-    sup_rows(in.Y, S);
+    sup_rows(Y, S);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
-        R.u[r] = (S[r][0] * wR + S[r][1] * wI + S[r][2] * x[2] + S[r][3] * x[3]) + in.res[r];
+        R.u[r] = (S[r][0] * wR + S[r][1] * wI + S[r][2] * x[2] + S[r][3] * x[3]) + res[r];
 #pragma unroll
     for (int i = 0; i < 4; ++i) R.u[4 + i] = x[2 + i];
-    // multipliers handed back to the SQP (..red_gpu.jl:256-277): tmpH = inv([LH_1h[0] LH_1i[0]; LH_1h[1] LH_1i[1]])
-    const double prod = in.LH_1h[0] * in.LH_1i[1] - in.LH_1i[0] * in.LH_1h[1];
-    const double t11 = in.LH_1i[1] / prod, t12 = -in.LH_1i[0] / prod, t21 = -in.LH_1h[1] / prod, t22 = in.LH_1h[0] / prod;
-    const double ti0 = 2 * R.u[0] * in.Y[2] + 2 * R.u[1] * (-in.Y[3]), ti1 = 2 * R.u[0] * in.Y[3] + 2 * R.u[1] * in.Y[2];
-    const double th0 = 2 * R.u[2] * in.Y[6] + 2 * R.u[3] * (-in.Y[7]), th1 = 2 * R.u[2] * (-in.Y[7]) + 2 * R.u[3] * (-in.Y[6]);
+    // multipliers handed back to the SQP: tmpH = inv([LH_1h[0] LH_1i[0]; LH_1h[1] LH_1i[1]])
+    const double prod = LH_1h[0] * LH_1i[1] - LH_1i[0] * LH_1h[1];
+    const double t11 = LH_1i[1] / prod, t12 = -LH_1i[0] / prod, t21 = -LH_1h[1] / prod, t22 = LH_1h[0] / prod;
+    const double ti0 = 2 * R.u[0] * Y[2] + 2 * R.u[1] * (-Y[3]), ti1 = 2 * R.u[0] * Y[3] + 2 * R.u[1] * Y[2];
+    const double th0 = 2 * R.u[2] * Y[6] + 2 * R.u[3] * (-Y[7]), th1 = 2 * R.u[2] * (-Y[7]) + 2 * R.u[3] * (-Y[6]);
+    const double (&trg)[N] = L.g;
     double w0 = trg[0] * ti0 + trg[1] * th0, w1 = trg[0] * ti1 + trg[1] * th1;
 #pragma unroll
     for (int k = 0; k < 6; ++k) w0 = EA_FMA(st[S_H0 + k], R.sqp[k], w0);
@@ -278,6 +314,25 @@ EA_DEV void solve(const Inputs &in, Store &st, const double (&x0)[4], const doub
     R.lambda[1] = -(t21 * w0 + t22 * w1);
     R.lambda[2] = -fabs(trg[0]);
     R.lambda[3] = -fabs(trg[1]);
+}
+
+// One branch to completion on one lane (host harness).
+template <class Store>
+EA_DEV void solve(const Inputs &in, Store &st, const double (&x0)[4], const double (&xl4)[4], const double (&xu4)[4],
+                  double &lam_j, double &lam_k, double &mu, int max_auglag, double mu_max, double scale,
+                  const branch::PowTable &T, Result &R) {
+    const double xl[N] = { 0.0, 0.0, xl4[0], xl4[1], xl4[2], xl4[3] };
+    const double xu[N] = { 200000.0, 200000.0, xu4[0], xu4[1], xu4[2], xu4[3] };
+    Lane L;
+    begin(L, in, st, x0, lam_j, lam_k, mu, T);
+#pragma unroll 1
+    for (;;) {
+        start_pass(L, st, scale);
+        if (step_pass(L, st, xl, xu, max_auglag, mu_max, T)) break;
+    }
+    const double h2[2] = { in.LH_1h[0], in.LH_1h[1] }, i2[2] = { in.LH_1i[0], in.LH_1i[1] };
+    finish(L, st, in.Y, in.res, h2, i2, R);
+    lam_j = L.lam_j; lam_k = L.lam_k; mu = L.mu;
 }
 
 }  // namespace qpsub
