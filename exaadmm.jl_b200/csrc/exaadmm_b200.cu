@@ -17,6 +17,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <mutex>
 #include <vector>
 
 using namespace ea;
@@ -150,12 +151,38 @@ template <typename H, typename T> int dev_alloc(H *h, T **p, size_t n) {
 template <typename H, typename T> int dev_upload(H *h, T **p, const std::vector<T> &v) {
     int rc = dev_alloc(h, p, v.size());
     if (rc) return rc;
+    // v may be a temporary: a copy from pageable memory returns once the source has been read into the driver's staging
+    // buffer (CUDA API synchronisation behaviour), so no stream synchronisation is needed before v goes away
     if (!v.empty()) CK(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));          // v may be a temporary: the copy must have left the host buffer
     return EA_OK;
 }
 
 inline int nblocks(int64_t n, int block) { return (int)std::max<int64_t>(1, (n + block - 1) / block); }
+
+// Upload straight from the caller's array (no host copy). A copy from pageable memory returns once the source has been
+// read, so the caller's buffer may change afterwards.
+template <typename H, typename T> int dev_upload_raw(H *h, T *dst, const T *src, size_t n) {
+    if (n) CK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return EA_OK;
+}
+
+// Pinned blocks for the control-block mirror are recycled across handles: drop-in callers create a handle per solve, and
+// a pinned allocation costs 1.3-2.5 ms each time.
+static std::mutex g_pin_mutex;
+static std::vector<void *> g_pin_free;
+constexpr size_t PIN_BLOCK = ((sizeof(Ctrl) + 4 * sizeof(double) + 255) / 256) * 256;
+static void *pin_acquire() {
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mutex);
+        if (!g_pin_free.empty()) { void *p = g_pin_free.back(); g_pin_free.pop_back(); return p; }
+    }
+    void *p = nullptr;
+    return cudaMallocHost(&p, PIN_BLOCK) == cudaSuccess ? p : nullptr;
+}
+static void pin_release(void *p) {
+    std::lock_guard<std::mutex> lk(g_pin_mutex);
+    if (g_pin_free.size() < 64) g_pin_free.push_back(p); else cudaFreeHost(p);
+}
 
 void build_pow_table(ea_handle *h, double mu_max) {
     if (h->pow_table_mu_max == mu_max) return;
@@ -333,14 +360,7 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
         if (slot_from[l] < 0 || slot_to[l] < 0) return bail(fail(h, EA_ERR_ARG, "ea_create: line %d is missing from FrIdx / ToIdx", l));
     for (int g = 0; g < ngen; ++g)
         if (slot_of_gen[g] < 0) return bail(fail(h, EA_ERR_ARG, "ea_create: generator %d is missing from GenIdx", g));
-    std::vector<int> ref2int((size_t)h->nvar);
-    for (int g = 0; g < ngen; ++g) { ref2int[2 * g] = 2 * slot_of_gen[g]; ref2int[2 * g + 1] = 2 * slot_of_gen[g] + 1; }
-    for (int l = 0; l < nline; ++l) {
-        const size_t base = 2 * (size_t)ngen + 8 * (size_t)l;
-        const int f = gpad + 4 * slot_from[l], t = gpad + 4 * slot_to[l];
-        ref2int[base + 0] = f + 0; ref2int[base + 1] = f + 1; ref2int[base + 2] = t + 0; ref2int[base + 3] = t + 1;
-        ref2int[base + 4] = f + 2; ref2int[base + 5] = t + 2; ref2int[base + 6] = f + 3; ref2int[base + 7] = t + 3;
-    }
+    // (the index map reference layout -> HBM layout, nvar entries, is derived from these on the device: k_build_ref2int)
 
     lap("layout (host)");
     // ---- device allocations -------------------------------------------------------------
@@ -359,30 +379,41 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     if ((rc = dev_upload(h, const_cast<int **>(&d.slot_to), slot_to))) return bail(rc);
     if ((rc = dev_upload(h, const_cast<int **>(&d.hstart), hstart))) return bail(rc);
     if ((rc = dev_upload(h, const_cast<int **>(&d.gstart), gstart))) return bail(rc);
-    if ((rc = dev_upload(h, &h->ref2int, ref2int))) return bail(rc);
+    {
+        int *sog = nullptr;
+        if ((rc = dev_upload(h, &sog, slot_of_gen))) return bail(rc);
+        if ((rc = dev_alloc(h, &h->ref2int, (size_t)h->nvar))) return bail(rc);
+        k_build_ref2int<<<nblocks(std::max(ngen, nline), 256), 256, 0, h->stream>>>(ngen, nline, gpad, sog, d.slot_from, d.slot_to, h->ref2int);
+        if (cudaGetLastError() != cudaSuccess) return bail(fail(h, EA_ERR_CUDA, "k_build_ref2int launch failed"));
+    }
     if ((rc = build_bus_warps(h, hstart, nbus))) return bail(rc);
 
     lap("index maps + bus warps");
-    {   // per line
-        std::vector<double> Y(8 * (size_t)nline), xlu(8 * (size_t)nline), rate(nline);
-        std::vector<int> brf(nline), brt(nline);
-        const double *ys[8] = { G->YffR, G->YffI, G->YftR, G->YftI, G->YttR, G->YttI, G->YtfR, G->YtfI };
+    {   // per line: the caller's arrays go up as they are; the bounds (interleaved lower / upper pairs) and the bus
+        // indices (1-based int64 pairs) are re-laid out on the device
         for (int l = 0; l < nline; ++l) {
-            for (int k = 0; k < 8; ++k) Y[(size_t)k * nline + l] = ys[k][l];
-            xlu[(size_t)0 * nline + l] = G->FrVmBound[2 * l]; xlu[(size_t)1 * nline + l] = G->FrVmBound[2 * l + 1];
-            xlu[(size_t)2 * nline + l] = G->ToVmBound[2 * l]; xlu[(size_t)3 * nline + l] = G->ToVmBound[2 * l + 1];
-            xlu[(size_t)4 * nline + l] = G->FrVaBound[2 * l]; xlu[(size_t)5 * nline + l] = G->FrVaBound[2 * l + 1];
-            xlu[(size_t)6 * nline + l] = G->ToVaBound[2 * l]; xlu[(size_t)7 * nline + l] = G->ToVaBound[2 * l + 1];
-            rate[l] = G->rateA[l];
             const int64_t fb = G->brBusIdx[2 * l] - 1, tb = G->brBusIdx[2 * l + 1] - 1;
             if (fb < 0 || fb >= nbus || tb < 0 || tb >= nbus) return bail(fail(h, EA_ERR_ARG, "ea_create: bad brBusIdx at line %d", l));
-            brf[l] = (int)fb; brt[l] = (int)tb;
         }
-        if ((rc = dev_upload(h, const_cast<double **>(&d.Y), Y))) return bail(rc);
-        if ((rc = dev_upload(h, const_cast<double **>(&d.xlu), xlu))) return bail(rc);
-        if ((rc = dev_upload(h, const_cast<double **>(&d.rateA), rate))) return bail(rc);
-        if ((rc = dev_upload(h, const_cast<int **>(&d.br_from), brf))) return bail(rc);
-        if ((rc = dev_upload(h, const_cast<int **>(&d.br_to), brt))) return bail(rc);
+        double *Yd = nullptr, *xlud = nullptr, *rated = nullptr, *raw = nullptr;
+        int *brfd = nullptr, *brtd = nullptr;
+        long long *idx = nullptr;
+        if ((rc = dev_alloc(h, &Yd, 8 * (size_t)nline)) || (rc = dev_alloc(h, &xlud, 8 * (size_t)nline)) ||
+            (rc = dev_alloc(h, &rated, (size_t)nline)) || (rc = dev_alloc(h, &brfd, (size_t)nline)) ||
+            (rc = dev_alloc(h, &brtd, (size_t)nline)) || (rc = dev_alloc(h, &raw, 8 * (size_t)nline)) ||
+            (rc = dev_alloc(h, &idx, 2 * (size_t)nline))) return bail(rc);
+        const double *ys[8] = { G->YffR, G->YffI, G->YftR, G->YftI, G->YttR, G->YttI, G->YtfR, G->YtfI };
+        for (int k = 0; k < 8; ++k)
+            if ((rc = dev_upload_raw(h, Yd + (size_t)k * nline, ys[k], (size_t)nline))) return bail(rc);
+        const double *bs[4] = { G->FrVmBound, G->ToVmBound, G->FrVaBound, G->ToVaBound };
+        for (int k = 0; k < 4; ++k)
+            if ((rc = dev_upload_raw(h, raw + (size_t)k * 2 * nline, bs[k], 2 * (size_t)nline))) return bail(rc);
+        if ((rc = dev_upload_raw(h, rated, G->rateA, (size_t)nline))) return bail(rc);
+        static_assert(sizeof(long long) == sizeof(int64_t), "brBusIdx is uploaded as 64-bit integers");
+        if ((rc = dev_upload_raw(h, idx, reinterpret_cast<const long long *>(G->brBusIdx), 2 * (size_t)nline))) return bail(rc);
+        k_layout_lines<<<nblocks(nline, 256), 256, 0, h->stream>>>(nline, raw, idx, xlud, brfd, brtd);
+        if (cudaGetLastError() != cudaSuccess) return bail(fail(h, EA_ERR_CUDA, "k_layout_lines launch failed"));
+        d.Y = Yd; d.xlu = xlud; d.rateA = rated; d.br_from = brfd; d.br_to = brtd;
         if ((rc = dev_alloc(h, &d.als, 3 * (size_t)nline))) return bail(rc);       // membuf rows 25-27 start at 0 (acopf_model.jl:87-88)
     }
     lap("per-line data");
@@ -425,8 +456,8 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
     h->nvar_global = h->nvar;
     {   // one pinned block for the control-block mirror and the 4 norms (a pinned allocation costs ~1.3 ms)
         static_assert(sizeof(Ctrl) % sizeof(double) == 0, "res_host follows ctrl_host in one pinned block");
-        void *pin = nullptr;
-        if (cudaMallocHost(&pin, sizeof(Ctrl) + 4 * sizeof(double)) != cudaSuccess) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
+        void *pin = pin_acquire();
+        if (!pin) return bail(fail(h, EA_ERR_ALLOC, "cudaMallocHost failed"));
         h->ctrl_host = static_cast<Ctrl *>(pin);
         h->res_host = reinterpret_cast<double *>(static_cast<char *>(pin) + sizeof(Ctrl));
     }
@@ -449,7 +480,7 @@ void ea_destroy(ea_handle_t *h) {
     if (h->gather_host) cudaFreeHost(h->gather_host);
     for (void *p : h->allocs) cudaFreeAsync(p, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);       // res_host lives in the same pinned block
+    if (h->ctrl_host) pin_release(h->ctrl_host);        // res_host lives in the same pinned block
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &e : h->kev) if (e) cudaEventDestroy(e);
     if (h->span0) cudaEventDestroy(h->span0);

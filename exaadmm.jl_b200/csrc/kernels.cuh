@@ -173,6 +173,31 @@ __device__ __forceinline__ bool grid_sum4(double (&acc)[4], double *partials, un
     return true;
 }
 
+// ea_create: the index map from the reference layout (2 per generator, 8 per line) to the HBM layout, and the per-line
+// constants re-laid out from the caller's arrays (interleaved bound pairs -> SoA rows, 1-based int64 bus pairs -> int).
+__global__ void k_build_ref2int(int ngen, int nline, int gpad, const int *slot_of_gen, const int *slot_from,
+                                const int *slot_to, int *ref2int) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ngen) { ref2int[2 * t] = 2 * slot_of_gen[t]; ref2int[2 * t + 1] = 2 * slot_of_gen[t] + 1; }
+    if (t < nline) {
+        int *r = ref2int + 2 * (size_t)ngen + 8 * (size_t)t;
+        const int f = gpad + 4 * slot_from[t], o = gpad + 4 * slot_to[t];
+        r[0] = f; r[1] = f + 1; r[2] = o; r[3] = o + 1; r[4] = f + 2; r[5] = o + 2; r[6] = f + 3; r[7] = o + 3;
+    }
+}
+__global__ void k_layout_lines(int nline, const double *raw /* 4 x (2 nline) */, const long long *bus_idx, double *xlu,
+                               int *br_from, int *br_to) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nline) return;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        xlu[(size_t)(2 * a) * nline + l] = raw[(size_t)a * 2 * nline + 2 * l];
+        xlu[(size_t)(2 * a + 1) * nline + l] = raw[(size_t)a * 2 * nline + 2 * l + 1];
+    }
+    br_from[l] = (int)(bus_idx[2 * l] - 1);
+    br_to[l] = (int)(bus_idx[2 * l + 1] - 1);
+}
+
 // ---------------------------------------------------------------------------
 // init_solution! (acopf_init_solution_gpu.jl:1-47): generator midpoints, flat-start
 // branch flows, rho_pq / rho_va. All other vectors are zeroed by the host first.
