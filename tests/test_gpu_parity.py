@@ -256,6 +256,29 @@ def test_graph_replay_equals_plain_launches(chunk):
         np.testing.assert_array_equal(a, b)
 
 
+def test_measurement_options_do_not_change_the_solve():
+    """bench.py's measurement modes - one CUDA-event bracket per kernel (kernel_timing = 1) or per iteration (2), the
+    L2 flushed before every iteration by a write (l2_flush_mb) or by a write + read (l2_flush_clean) - only time the
+    loop: same stopping iteration and the same state bit for bit as the plain graph loop."""
+    d = synthetic_case(300, 40, 420, seed=301)
+    outs = []
+    for kt, mb, clean in ((0, 0, 0), (1, 8, 0), (2, 8, 1)):
+        env = AdmmEnv(d, 4e2, 4e4, use_gpu=True, verbose=0)
+        mod = ModelAcopf(env)
+        mod.set_option("kernel_timing", kt)
+        mod.set_option("l2_flush_mb", mb)
+        mod.set_option("l2_flush_clean", clean)
+        env.params.outer_iterlim = 2; env.params.inner_iterlim = 150
+        admm_two_level(env, mod, None, mode="native")
+        outs.append((mod.info.outer, mod.info.cumul, mod.info.status, mod.info.objval, mod.solution.u_curr,
+                     mod.solution.z_curr, mod.solution.l_curr))
+        mod.close()
+    for o in outs[1:]:
+        assert o[:4] == outs[0][:4]
+        for x, y in zip(o[4:], outs[0][4:]):
+            np.testing.assert_array_equal(x, y)
+
+
 def test_vector_and_membuf_round_trip(case9_grid):
     env, mod = _env_mod(ea.CASE9)
     rng = np.random.default_rng(0)
