@@ -353,8 +353,11 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
     L.phase = (lane < lanes_on) ? branch::NEED : branch::DONE;
     L.step_pending = false;
     int I = -1;
-    unsigned work[7] = { 0, 0, 0, 0, 0, 0, 0 };            // calls, auglag, evals, cg, shifts, rejected, hit_max (per lane: 32 bits)
-    int mx = 0;
+    // work of this CTA: calls, auglag, evals, cg, shifts, rejected, hit_max, max evals of a branch - in shared memory
+    // (a finishing lane adds its branch), not in eight registers per lane that would stay live across the whole loop
+    __shared__ unsigned s_work[8];
+    if (threadIdx.x < 8) s_work[threadIdx.x] = 0u;
+    __syncthreads();
 
 #pragma unroll 1
     for (;;) {
@@ -384,9 +387,14 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
             load_bounds(col, xl, xu);
             if (branch::eval_pass(L, eval, pass, xl, xu, max_auglag, mu_max, T)) {
                 store_branch(d, I, L);
-                work[0] += 1; work[1] += L.it_al; work[2] += L.evals; work[3] += L.cg; work[4] += L.shifts;
-                work[5] += L.rejected; work[6] += L.hit_max;
-                mx = max(mx, L.evals);
+                if (d.count_work) {
+                    atomicAdd(&s_work[0], 1u); atomicAdd(&s_work[1], (unsigned)L.it_al); atomicAdd(&s_work[2], (unsigned)L.evals);
+                    atomicAdd(&s_work[3], (unsigned)L.cg);
+                    if (L.shifts) atomicAdd(&s_work[4], (unsigned)L.shifts);
+                    if (L.rejected) atomicAdd(&s_work[5], (unsigned)L.rejected);
+                    if (L.hit_max) atomicAdd(&s_work[6], (unsigned)L.hit_max);
+                    atomicMax(&s_work[7], (unsigned)L.evals);
+                }
                 L.phase = branch::NEED;
             }
         }
@@ -405,17 +413,9 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
         atomicMax(&d.counters->t[2], t_now);
     }
     if (d.count_work) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 7; ++k) work[k] += __shfl_down_sync(full, work[k], o);
-            mx = max(mx, __shfl_down_sync(full, mx, o));
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 7; ++k) if (work[k]) atomicAdd(&d.counters->v[k], (unsigned long long)work[k]);
-            atomicMax(&d.counters->v[7], (unsigned long long)mx);
-        }
+        __syncthreads();
+        if (threadIdx.x < 7) { if (s_work[threadIdx.x]) atomicAdd(&d.counters->v[threadIdx.x], (unsigned long long)s_work[threadIdx.x]); }
+        else if (threadIdx.x == 7) atomicMax(&d.counters->v[7], (unsigned long long)s_work[7]);
     }
 }
 
