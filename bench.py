@@ -488,7 +488,7 @@ def run_ours(args, rank, world, local_rank):
         """init -> W warm-up iterations -> K timed iterations of the same solve trajectory."""
         mod, h, lg, _ = new_handle()
         check(lib.ea_init_solution(h, rho_pq, rho_va), h)
-        check(lib.ea_set_option(h, b"count_work", 1.0 if kernel_timing else 0.0), h)
+        check(lib.ea_set_option(h, b"count_work", 1.0 if kernel_timing == 1 else 0.0), h)    # the counters feed the rooflines (pass B)
         drv = Driver(h, lg.nline)
         drv.run(args.warmup)
         check(lib.ea_reset_counters(h), h)

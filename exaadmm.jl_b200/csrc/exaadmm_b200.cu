@@ -222,7 +222,10 @@ int launch_x(ea_handle *h, long long major, int zsel, int max_auglag, double mu_
     // one lane per branch at least: small grids are spread over all resident warps (k_xupdate: lanes_on)
     const int64_t work_blocks = std::max<int64_t>((h->nline + XBLOCK / 32 - 1) / (XBLOCK / 32), (h->ngen + XBLOCK - 1) / XBLOCK);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->x_resident_blocks, work_blocks));
-    k_xupdate<<<grid, XBLOCK, XTILE_BYTES, stream>>>(h->d, h->pow_table, major, zsel, max_auglag, mu_max, scale, lines, gens);
+    if (h->d.count_work)
+        k_xupdate<true><<<grid, XBLOCK, XTILE_BYTES, stream>>>(h->d, h->pow_table, major, zsel, max_auglag, mu_max, scale, lines, gens);
+    else
+        k_xupdate<false><<<grid, XBLOCK, XTILE_BYTES, stream>>>(h->d, h->pow_table, major, zsel, max_auglag, mu_max, scale, lines, gens);
     CK(cudaGetLastError());
     h->n_x++;
     return EA_OK;
@@ -308,8 +311,9 @@ int ea_create(const ea_grid_t *G, int device, ea_handle_t **out) {
 
     {
         int per_sm = 0, sms = 0;
-        if (cudaFuncSetAttribute(k_xupdate, cudaFuncAttributeMaxDynamicSharedMemorySize, XTILE_BYTES) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xupdate, XBLOCK, XTILE_BYTES) != cudaSuccess ||
+        if (cudaFuncSetAttribute(k_xupdate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, XTILE_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_xupdate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, XTILE_BYTES) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xupdate<true>, XBLOCK, XTILE_BYTES) != cudaSuccess ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1)
             return bail(fail(h, EA_ERR_CUDA, "k_xupdate occupancy query failed: %s", cudaGetErrorString(cudaGetLastError())));
         h->x_resident_blocks = per_sm * sms;

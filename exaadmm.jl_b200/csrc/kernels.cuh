@@ -319,6 +319,9 @@ __device__ __forceinline__ void store_branch(const Dev &d, int I, const branch::
     d.als[I] = L.ls[0]; d.als[nl + I] = L.ls[1]; d.als[2 * nl + I] = L.mu;
 }
 
+// COUNT = false: the launch without work counters (option "count_work" = 0): the per-branch tallies of the lane state
+// (CG iterations, shifts, rejected steps ...) are then dead code and their registers free.
+template <bool COUNT>
 __global__ void __launch_bounds__(XBLOCK, EA_XMINB)
 k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_auglag, double mu_max, double scale,
           int do_lines, int do_gens) {
@@ -337,7 +340,7 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     unsigned long long t_now = 0;
-    if (d.count_work > 1 && threadIdx.x == 0) {
+    if (COUNT && d.count_work > 1 && threadIdx.x == 0) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
         atomicMin(&d.counters->t[0], t_now);
     }
@@ -375,7 +378,7 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
                     if (I < d.nline) { load_branch(d, z, I, major, col, L); branch::begin(L, T); }
                     else {
                         L.phase = branch::DONE;
-                        if (d.count_work > 1 && !saw_empty) {
+                        if (COUNT && d.count_work > 1 && !saw_empty) {
                             saw_empty = true;
                             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
                             atomicMin(&d.counters->t[1], t_now);
@@ -387,7 +390,7 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
             load_bounds(col, xl, xu);
             if (branch::eval_pass(L, eval, pass, xl, xu, max_auglag, mu_max, T)) {
                 store_branch(d, I, L);
-                if (d.count_work) {
+                if (COUNT && d.count_work) {
                     atomicAdd(&s_work[0], 1u); atomicAdd(&s_work[1], (unsigned)L.it_al); atomicAdd(&s_work[2], (unsigned)L.evals);
                     atomicAdd(&s_work[3], (unsigned)L.cg);
                     if (L.shifts) atomicAdd(&s_work[4], (unsigned)L.shifts);
@@ -408,11 +411,11 @@ k_xupdate(Dev d, branch::PowTable T, long long major_arg, int zsel_arg, int max_
         branch::compute(L, xl, xu);
     }
 
-    if (d.count_work > 1 && lane == 0) {
+    if (COUNT && d.count_work > 1 && lane == 0) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
         atomicMax(&d.counters->t[2], t_now);
     }
-    if (d.count_work) {
+    if (COUNT && d.count_work) {
         __syncthreads();
         if (threadIdx.x < 7) { if (s_work[threadIdx.x]) atomicAdd(&d.counters->v[threadIdx.x], (unsigned long long)s_work[threadIdx.x]); }
         else if (threadIdx.x == 7) atomicMax(&d.counters->v[7], (unsigned long long)s_work[7]);

@@ -800,7 +800,7 @@ template <int N> EA_DEV void compute_step_auto(double (&x)[N], const double (&xl
 #if defined(EA_STATS) && !defined(__CUDA_ARCH__)
     g_stat_first = (evals_so_far < 2) ? 1 : 0;        // [1]: the first step of a problem
 #endif
-    if (EA_FAST_EVALS > 0 && evals_so_far >= EA_FAST_EVALS &&
+    if (EA_FAST_EVALS > 0 && (EA_FAST_EVALS == 1 || evals_so_far >= EA_FAST_EVALS) &&
         newton_step<N>(x, xl, xu, A, g, delta, alphac, prered, gts, snorm, st)) return;
     compute_step<N>(x, xl, xu, A, g, delta, alphac, prered, gts, snorm, st);
 }

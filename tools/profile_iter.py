@@ -2,6 +2,7 @@
 """Run W + K fused inner iterations of a workload (for ncu / quick timing).
 usage: python tools/profile_iter.py [workload] [warmup] [steps] [chunk]"""
 import ctypes as C
+import os
 import sys
 import time
 from pathlib import Path
@@ -24,6 +25,7 @@ h = C.c_void_p()
 assert lib.ea_create(C.byref(gs), 0, C.byref(h)) == 0, lib.ea_last_error(None)
 assert lib.ea_init_solution(h, rho_pq, rho_va) == 0
 lib.ea_set_option(h, b"chunk", float(chunk))
+lib.ea_set_option(h, b"count_work", float(os.environ.get("EA_COUNT_WORK", "1")))
 import os
 lib.ea_set_option(h, b"use_graph", float(os.environ.get("EA_USE_GRAPH", "1")))
 res = np.zeros(4); got = C.c_int64(); nz = C.c_double()
