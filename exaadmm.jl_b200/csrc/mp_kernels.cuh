@@ -129,8 +129,10 @@ k_xupdate_mp(MpDev m, BatchView bv, int nline, branch::PowTable T, long long maj
     L.phase = branch::NEED;
     L.step_pending = false;
     int G = -1;                                             // (period, branch) pair of this lane: G = t * nline + I
-    unsigned long long work[7] = { 0, 0, 0, 0, 0, 0, 0 };
-    int mx = 0;
+    // work of this CTA in shared memory (a finishing lane adds its branch), not in registers live across the whole loop
+    __shared__ unsigned s_work[8];
+    if (threadIdx.x < 8) s_work[threadIdx.x] = 0u;
+    __syncthreads();
     Counters *counters = m.devs[0].counters;
     const int count_work = m.devs[0].count_work;
 
@@ -166,9 +168,14 @@ k_xupdate_mp(MpDev m, BatchView bv, int nline, branch::PowTable T, long long maj
             if (branch::eval_pass(L, eval, pass, xl, xu, max_auglag, mu_max, T)) {
                 const int a = G / nline;
                 store_branch(m.devs[BATCH ? bv.active[a] : a], G - a * nline, L);
-                work[0] += 1; work[1] += L.it_al; work[2] += L.evals; work[3] += L.cg; work[4] += L.shifts;
-                work[5] += L.rejected; work[6] += L.hit_max;
-                mx = max(mx, L.evals);
+                if (count_work) {
+                    atomicAdd(&s_work[0], 1u); atomicAdd(&s_work[1], (unsigned)L.it_al); atomicAdd(&s_work[2], (unsigned)L.evals);
+                    atomicAdd(&s_work[3], (unsigned)L.cg);
+                    if (L.shifts) atomicAdd(&s_work[4], (unsigned)L.shifts);
+                    if (L.rejected) atomicAdd(&s_work[5], (unsigned)L.rejected);
+                    if (L.hit_max) atomicAdd(&s_work[6], (unsigned)L.hit_max);
+                    atomicMax(&s_work[7], (unsigned)L.evals);
+                }
                 L.phase = branch::NEED;
             }
         }
@@ -180,17 +187,9 @@ k_xupdate_mp(MpDev m, BatchView bv, int nline, branch::PowTable T, long long maj
         branch::compute(L, xl, xu);
     }
     if (count_work) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 7; ++k) work[k] += __shfl_down_sync(full, work[k], o);
-            mx = max(mx, __shfl_down_sync(full, mx, o));
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 7; ++k) if (work[k]) atomicAdd(&counters->v[k], work[k]);
-            atomicMax(&counters->v[7], (unsigned long long)mx);
-        }
+        __syncthreads();
+        if (threadIdx.x < 7) { if (s_work[threadIdx.x]) atomicAdd(&counters->v[threadIdx.x], (unsigned long long)s_work[threadIdx.x]); }
+        else if (threadIdx.x == 7) atomicMax(&counters->v[7], (unsigned long long)s_work[7]);
     }
 }
 
