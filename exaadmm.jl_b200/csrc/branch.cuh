@@ -44,7 +44,28 @@ __host__ __device__ __forceinline__ long long ea_clock() {
 namespace branch {
 
 constexpr int N = 6;
-using Sym6 = tron::Sym<N>;
+// The Hessian of the branch objective in its 15 independent entries. Of the 21 entries of the packed lower triangle
+// six follow from the others - the objective depends on the angles through t_i - t_j only, and each slack enters one
+// constraint linearly: a30 = -a20, a31 = -a21, a43 = -a42, a53 = -a52, a54 = 0, a55 = a44 - and the TRON routines read a
+// matrix through at(i, j) with compile-time indices, so the negations become operand modifiers and the zero drops out:
+// twelve registers less in the lane state (the branch kernel sits at the 255-register cap) and a few multiply-adds less
+// per matrix-vector product, with bit-identical results.
+struct Hess {
+    double a00, a10, a11, a20, a21, a22, a32, a33, a40, a41, a42, a44, a50, a51, a52;
+    EA_DEV double at(int i, int j) const {
+        const int k = tron::tri(i, j);
+        return k == 0 ? a00 : k == 1 ? a10 : k == 2 ? a11 : k == 3 ? a20 : k == 4 ? a21 : k == 5 ? a22
+             : k == 6 ? -a20 : k == 7 ? -a21 : k == 8 ? a32 : k == 9 ? a33
+             : k == 10 ? a40 : k == 11 ? a41 : k == 12 ? a42 : k == 13 ? -a42 : k == 14 ? a44
+             : k == 15 ? a50 : k == 16 ? a51 : k == 17 ? a52 : k == 18 ? -a52 : k == 19 ? 0.0 : a44;
+    }
+    // from a full 6 x 6 matrix with that structure (row-major; the oracle's Hessian in the host harness)
+    EA_DEV void from_dense(const double *H) {
+        a00 = H[0]; a10 = H[6]; a11 = H[7]; a20 = H[12]; a21 = H[13]; a22 = H[14]; a32 = H[20]; a33 = H[21];
+        a40 = H[24]; a41 = H[25]; a42 = H[26]; a44 = H[28]; a50 = H[30]; a51 = H[31]; a52 = H[32];
+    }
+};
+using Sym6 = Hess;
 
 struct Data {          // per-branch inputs, reference rows in comments (membuf rows 1-24, acopf_auglag..gpu.jl:50-73)
     double lam[8];     // rows 1-8   lambda   (pij,qij,pji,qji,wi,wj,ti,tj)
@@ -200,28 +221,23 @@ EA_DEV void eval_fgh_ref(const View &D, const double (&ls)[2], double mu, double
     g[3] = scale * (-gy[2] + D.lam(7) + D.rho(7) * (x[3] - D.xt(7)));
     g[4] = scale * m[0];
     g[5] = scale * m[1];
-    using tron::tri;
-    A.a[tri(0, 0)] = scale * Hy[0][0];
-    A.a[tri(1, 0)] = scale * Hy[0][1];
-    A.a[tri(1, 1)] = scale * Hy[1][1];
-    A.a[tri(2, 0)] = scale * Hy[0][2];
-    A.a[tri(2, 1)] = scale * Hy[1][2];
-    A.a[tri(2, 2)] = scale * (Hy[2][2] + D.rho(6));
-    A.a[tri(3, 0)] = scale * (-Hy[0][2]);
-    A.a[tri(3, 1)] = scale * (-Hy[1][2]);
-    A.a[tri(3, 2)] = scale * (-Hy[2][2]);
-    A.a[tri(3, 3)] = scale * (Hy[2][2] + D.rho(7));
-    A.a[tri(4, 0)] = scale * (mu * d[0][0]);
-    A.a[tri(4, 1)] = scale * (mu * d[0][1]);
-    A.a[tri(4, 2)] = scale * (mu * d[0][2]);
-    A.a[tri(4, 3)] = scale * (-mu * d[0][2]);
-    A.a[tri(4, 4)] = scale * mu;
-    A.a[tri(5, 0)] = scale * (mu * d[1][0]);
-    A.a[tri(5, 1)] = scale * (mu * d[1][1]);
-    A.a[tri(5, 2)] = scale * (mu * d[1][2]);
-    A.a[tri(5, 3)] = scale * (-mu * d[1][2]);
-    A.a[tri(5, 4)] = 0.0;
-    A.a[tri(5, 5)] = scale * mu;
+    A.a00 = scale * Hy[0][0];
+    A.a10 = scale * Hy[0][1];
+    A.a11 = scale * Hy[1][1];
+    A.a20 = scale * Hy[0][2];
+    A.a21 = scale * Hy[1][2];
+    A.a22 = scale * (Hy[2][2] + D.rho(6));
+    A.a32 = scale * (-Hy[2][2]);
+    A.a33 = scale * (Hy[2][2] + D.rho(7));
+    A.a40 = scale * (mu * d[0][0]);
+    A.a41 = scale * (mu * d[0][1]);
+    A.a42 = scale * (mu * d[0][2]);
+    A.a44 = scale * mu;
+    A.a50 = scale * (mu * d[1][0]);
+    A.a51 = scale * (mu * d[1][1]);
+    A.a52 = scale * (mu * d[1][2]);
+    // (a30 = scale * (-Hy02), a31 = scale * (-Hy12), a43 = scale * (-mu d02), a53 = scale * (-mu d12), a54 = 0,
+    //  a55 = scale * mu in the oracle: exactly the negatives / copies that Hess::at returns)
 }
 #endif
 
@@ -331,29 +347,22 @@ EA_DEV void eval_hess(const View &D, const Pre &p, const Wsum &W, const double (
     H00 += 2.0 * W.ri + 4.0 * rho4 * vi2;
     H11 += 2.0 * W.rj + 4.0 * rho5 * vj2;
 
-    using tron::tri;
     const double smu = scale * mu;
-    A.a[tri(0, 0)] = scale * H00;
-    A.a[tri(1, 0)] = scale * H01;
-    A.a[tri(1, 1)] = scale * H11;
-    A.a[tri(2, 0)] = scale * H02;
-    A.a[tri(2, 1)] = scale * H12;
-    A.a[tri(2, 2)] = scale * (H22 + rho6);
-    A.a[tri(3, 0)] = -(scale * H02);
-    A.a[tri(3, 1)] = -(scale * H12);
-    A.a[tri(3, 2)] = -(scale * H22);
-    A.a[tri(3, 3)] = scale * (H22 + rho7);
-    A.a[tri(4, 0)] = smu * d[0][0];
-    A.a[tri(4, 1)] = smu * d[0][1];
-    A.a[tri(4, 2)] = smu * d[0][2];
-    A.a[tri(4, 3)] = -(smu * d[0][2]);
-    A.a[tri(4, 4)] = smu;
-    A.a[tri(5, 0)] = smu * d[1][0];
-    A.a[tri(5, 1)] = smu * d[1][1];
-    A.a[tri(5, 2)] = smu * d[1][2];
-    A.a[tri(5, 3)] = -(smu * d[1][2]);
-    A.a[tri(5, 4)] = 0.0;
-    A.a[tri(5, 5)] = smu;
+    A.a00 = scale * H00;
+    A.a10 = scale * H01;
+    A.a11 = scale * H11;
+    A.a20 = scale * H02;
+    A.a21 = scale * H12;
+    A.a22 = scale * (H22 + rho6);
+    A.a32 = -(scale * H22);
+    A.a33 = scale * (H22 + rho7);
+    A.a40 = smu * d[0][0];
+    A.a41 = smu * d[0][1];
+    A.a42 = smu * d[0][2];
+    A.a44 = smu;
+    A.a50 = smu * d[1][0];
+    A.a51 = smu * d[1][1];
+    A.a52 = smu * d[1][2];
 }
 
 // The whole evaluation at once (diagnostics, unit tests; the parity build's only form).

@@ -869,7 +869,7 @@ __global__ void k_diag_eval(int n, const double *x, const double *param, const d
     for (int a = 0; a < 6; ++a) {
         g[6 * (size_t)i + a] = gg[a];
 #pragma unroll
-        for (int b = 0; b < 6; ++b) H[36 * (size_t)i + 6 * a + b] = A.a[tron::tri(a, b)];
+        for (int b = 0; b < 6; ++b) H[36 * (size_t)i + 6 * a + b] = A.at(a, b);
     }
 }
 

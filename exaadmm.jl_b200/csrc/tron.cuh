@@ -109,7 +109,12 @@ EA_DEV double dsqrt(double a) {             // a >= 0
 
 __host__ __device__ constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-template <int N> struct Sym { double a[N * (N + 1) / 2]; };   // packed lower triangle
+// Symmetric matrices are read through at(i, j) (compile-time indices in the unrolled loops), so that a problem whose
+// Hessian has structure can hand in a type that stores only its independent entries (branch::Hess: 15 of 21).
+template <int N> struct Sym {                                 // packed lower triangle
+    double a[N * (N + 1) / 2];
+    EA_DEV double at(int i, int j) const { return a[tri(i, j)]; }
+};
 // Cholesky factor: packed lower triangle + reciprocal diagonal (so that the many
 // triangular solves multiply instead of divide)
 template <int N> struct Chol { double a[N * (N + 1) / 2]; double rd[N]; };
@@ -133,12 +138,12 @@ EA_DEV bool norm_le(double sumsq, double bound) {
 }
 
 // y = A x  (A packed symmetric)
-template <int N> EA_DEV void symv(const Sym<N> &A, const double (&x)[N], double (&y)[N]) {
+template <int N, class M> EA_DEV void symv(const M &A, const double (&x)[N], double (&y)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < N; ++j) s = EA_FMA(A.a[tri(i, j)], x[j], s);
+        for (int j = 0; j < N; ++j) s = EA_FMA(A.at(i, j), x[j], s);
         y[i] = s;
     }
 }
@@ -211,7 +216,7 @@ template <int N> EA_DEV double trqsol(const double (&x)[N], const double (&p)[N]
 }
 
 // q(s) = 0.5 s'As + g's and g's
-template <int N> EA_DEV void quad(const Sym<N> &A, const double (&g)[N], const double (&s)[N],
+template <int N, class M> EA_DEV void quad(const M &A, const double (&g)[N], const double (&s)[N],
                                                       double &q, double &gts) {
     double w[N];
     symv<N>(A, s, w);
@@ -222,8 +227,8 @@ template <int N> EA_DEV void quad(const Sym<N> &A, const double (&g)[N], const d
 // Cauchy step (B.2 dcauchy). Returns the new alpha; s is the step. One loop with a
 // single projected-step / quadratic-model site (the three phases of the original:
 // first trial, interpolation, extrapolation) to keep the instruction footprint small.
-template <int N> EA_DEV double cauchy(const double (&x)[N], const double (&xl)[N], const double (&xu)[N],
-                                                          const Sym<N> &A, const double (&g)[N], double delta,
+template <int N, class M> EA_DEV double cauchy(const double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                          const M &A, const double (&g)[N], double delta,
                                                           double alpha, double (&s)[N]) {
     const double mu0 = 0.01, interpf = 0.1, extrapf = 10.0;
     double brptmin, brptmax;
@@ -333,7 +338,7 @@ template <int N> __host__ __device__ __noinline__ void icfs_general(const Sym<N>
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const bool fr = (freemask >> i) & 1u;
-        const double aii = A.a[tri(i, i)];
+        const double aii = A.at(i, i);
         wa2[i] = 1.0;
         if (fr && aii > 0.0) {
 #if EA_EXACT
@@ -345,7 +350,7 @@ template <int N> __host__ __device__ __noinline__ void icfs_general(const Sym<N>
             double cs = 0.0;
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-                const double akj = ((freemask >> k) & 1u) ? A.a[tri(k, i)] : 0.0;
+                const double akj = ((freemask >> k) & 1u) ? A.at(k, i) : 0.0;
                 cs = EA_FMA(akj, akj, cs);
             }
             wa2[i] = 1.0 / sqrt(sqrt(cs));
@@ -354,7 +359,7 @@ template <int N> __host__ __device__ __noinline__ void icfs_general(const Sym<N>
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         if ((freemask >> i) & 1u) {
-            const double aii = A.a[tri(i, i)];
+            const double aii = A.at(i, i);
             if (aii == 0.0) alpha = alphas;
             else alpha = dmax(alpha, -aii * (wa2[i] * wa2[i]));
         }
@@ -370,7 +375,7 @@ template <int N> __host__ __device__ __noinline__ void icfs_general(const Sym<N>
             for (int j = 0; j <= i; ++j) {
                 const bool fj = (freemask >> j) & 1u;
                 double v;
-                if (fi && fj) v = A.a[tri(i, j)] * wa2[i] * wa2[j] + ((i == j) ? alpha : 0.0);
+                if (fi && fj) v = A.at(i, j) * wa2[i] * wa2[j] + ((i == j) ? alpha : 0.0);
                 else v = (i == j) ? 1.0 : 0.0;
                 L.a[tri(i, j)] = v;
             }
@@ -394,13 +399,13 @@ template <int N> __host__ __device__ __noinline__ void icfs_general(const Sym<N>
 // dicfs, common case first: every free diagonal entry is positive and the unshifted
 // factorization succeeds (then the general algorithm does exactly this single attempt).
 // Returns true if the general path (shift search) had to run.
-template <int N> EA_DEV bool icfs(const Sym<N> &A, unsigned freemask, Chol<N> &L) {
+template <int N, class M> EA_DEV bool icfs(const M &A, unsigned freemask, Chol<N> &L) {
     double wa2[N];
     bool pos = true;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const bool fr = (freemask >> i) & 1u;
-        const double aii = A.a[tri(i, i)];
+        const double aii = A.at(i, i);
         pos = pos && (!fr || aii > 0.0);
 #if EA_EXACT
         wa2[i] = fr ? 1.0 / sqrt(aii) : 1.0;
@@ -415,7 +420,7 @@ template <int N> EA_DEV bool icfs(const Sym<N> &A, unsigned freemask, Chol<N> &L
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
                 const bool fj = (freemask >> j) & 1u;
-                L.a[tri(i, j)] = (fi && fj) ? A.a[tri(i, j)] * wa2[i] * wa2[j] + 0.0 : ((i == j) ? 1.0 : 0.0);
+                L.a[tri(i, j)] = (fi && fj) ? A.at(i, j) * wa2[i] * wa2[j] + 0.0 : ((i == j) ? 1.0 : 0.0);
             }
         }
         if (cholesky<N>(L)) {
@@ -426,7 +431,7 @@ template <int N> EA_DEV bool icfs(const Sym<N> &A, unsigned freemask, Chol<N> &L
                 for (int j = 0; j <= i; ++j) L.a[tri(i, j)] = L.a[tri(i, j)] / wa2[i];
 #else
                 const bool fi = (freemask >> i) & 1u;
-                const double si = fi ? A.a[tri(i, i)] * wa2[i] : 1.0;     // sqrt(a_ii) = a_ii * rsqrt(a_ii)
+                const double si = fi ? A.at(i, i) * wa2[i] : 1.0;     // sqrt(a_ii) = a_ii * rsqrt(a_ii)
 #pragma unroll
                 for (int j = 0; j <= i; ++j) L.a[tri(i, j)] = L.a[tri(i, j)] * si;
                 L.rd[i] = L.rd[i] * wa2[i];
@@ -436,7 +441,11 @@ template <int N> EA_DEV bool icfs(const Sym<N> &A, unsigned freemask, Chol<N> &L
         }
     }
     {   // rare: go through addressable copies so that A and L themselves stay in registers
-        Sym<N> A2 = A;
+        Sym<N> A2;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) A2.a[tri(i, j)] = A.at(i, j);
         Chol<N> L2;
         icfs_general<N>(A2, freemask, L2);
         L = L2;
@@ -445,7 +454,7 @@ template <int N> EA_DEV bool icfs(const Sym<N> &A, unsigned freemask, Chol<N> &L
 }
 
 // B.4 dtrpcg on the masked system. w is the solution in the L-transformed space.
-template <int N> EA_DEV void trpcg(const Sym<N> &A, unsigned freemask, const double (&g)[N], double delta,
+template <int N, class M> EA_DEV void trpcg(const M &A, unsigned freemask, const double (&g)[N], double delta,
                                                        const Chol<N> &L, double tol, double stol, int itermax,
                                                        double (&w)[N], int &iters, int &info) {
     double t[N], r[N], p[N], q[N], z[N];
@@ -488,8 +497,8 @@ template <int N> EA_DEV void trpcg(const Sym<N> &A, unsigned freemask, const dou
 }
 
 // B.6 dprsrch on the masked system (w is zero on fixed variables).
-template <int N> EA_DEV void prsrch(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
-                                                        const Sym<N> &A, const double (&g)[N], double (&w)[N]) {
+template <int N, class M> EA_DEV void prsrch(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                        const M &A, const double (&g)[N], double (&w)[N]) {
     const double mu0 = 0.01, interpf = 0.5;
     double wa1[N], brptmin, brptmax, alpha = 1.0, q, gts;
     bool search = true;
@@ -513,8 +522,8 @@ template <int N> EA_DEV void prsrch(double (&x)[N], const double (&xl)[N], const
 struct Stats { int cg = 0; int shifts = 0; };
 
 // B.3 dspcg: from the Cauchy step s, move x to the trial point; s becomes x_trial - x_0.
-template <int N> EA_DEV void spcg(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
-                                                      const Sym<N> &A, const double (&g)[N], double delta, double rtol,
+template <int N, class M> EA_DEV void spcg(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                      const M &A, const double (&g)[N], double delta, double rtol,
                                                       double (&s)[N], int itermax, Stats &st) {
     double w[N];
     symv<N>(A, s, w);
@@ -565,8 +574,8 @@ template <int N> EA_DEV void spcg(double (&x)[N], const double (&xl)[N], const d
 // One "COMPUTE" of dtron (B.0): Cauchy point + projected CG. On entry x is the
 // current iterate; on exit x is the trial point, prered the predicted reduction,
 // gts = g's and snorm = |s| for the step s = trial - x_c.
-template <int N> EA_DEV void compute_step(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
-                                                              const Sym<N> &A, const double (&g)[N], double delta,
+template <int N, class M> EA_DEV void compute_step(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                                              const M &A, const double (&g)[N], double delta,
                                                               double &alphac, double &prered, double &gts, double &snorm,
                                                               Stats &st) {
     const double cgtol = 0.1;
@@ -581,14 +590,14 @@ template <int N> EA_DEV void compute_step(double (&x)[N], const double (&xl)[N],
 
 // Plain Cholesky of the masked matrix (fixed rows / columns replaced by the identity), no scaling, no shift search.
 // false if a pivot is not positive.
-template <int N> EA_DEV bool chol_masked(const Sym<N> &A, unsigned freemask, Chol<N> &L) {
+template <int N, class M> EA_DEV bool chol_masked(const M &A, unsigned freemask, Chol<N> &L) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const bool fi = (freemask >> i) & 1u;
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
             const bool fj = (freemask >> j) & 1u;
-            L.a[tri(i, j)] = (fi && fj) ? A.a[tri(i, j)] : ((i == j) ? 1.0 : 0.0);
+            L.a[tri(i, j)] = (fi && fj) ? A.at(i, j) : ((i == j) ? 1.0 : 0.0);
         }
     }
     return cholesky<N>(L);
@@ -614,8 +623,8 @@ template <int N> EA_DEV bool chol_masked(const Sym<N> &A, unsigned freemask, Cho
 // with the literal path to rounding (the same vectors computed with fewer operations), decisions except within rounding
 // of a tie (tests/test_device_code_on_host.py::test_direct_step_follows_the_literal_algorithm); EA_EXACT builds never
 // take it.
-template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
-                                         const Sym<N> &A, const double (&g)[N], double delta,
+template <int N, class M> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                         const M &A, const double (&g)[N], double delta,
                                          double &alphac, double &prered, double &gts, double &snorm, Stats &st) {
 #if EA_EXACT
     return false;
@@ -793,8 +802,8 @@ template <int N> EA_DEV bool newton_step(double (&x)[N], const double (&xl)[N], 
 #ifndef EA_FAST_EVALS
 #define EA_FAST_EVALS 1
 #endif
-template <int N> EA_DEV void compute_step_auto(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
-                                               const Sym<N> &A, const double (&g)[N], double delta,
+template <int N, class M> EA_DEV void compute_step_auto(double (&x)[N], const double (&xl)[N], const double (&xu)[N],
+                                               const M &A, const double (&g)[N], double delta,
                                                double &alphac, double &prered, double &gts, double &snorm,
                                                Stats &st, int evals_so_far) {
 #if defined(EA_STATS) && !defined(__CUDA_ARCH__)

@@ -32,7 +32,7 @@ struct OracleEval {
         double H[36];
         f = fn(x, param, Y, scale);
         ghn(x, param, Y, scale, g, H);
-        for (int a = 0; a < 6; ++a) for (int b = 0; b <= a; ++b) A.a[tron::tri(a, b)] = H[6 * a + b];
+        A.from_dense(H);
         const double cc = x[0] * x[1] * cos(x[2] - x[3]), ss = x[0] * x[1] * sin(x[2] - x[3]);
         F[0] = Y[0] * (x[0] * x[0]) + Y[2] * cc + Y[3] * ss;        // as the oracle's AL loop computes them
         F[1] = -Y[1] * (x[0] * x[0]) - Y[3] * cc + Y[2] * ss;
@@ -93,7 +93,7 @@ void hh_eval(const double *x, const double *param, const double *Y, double scale
     for (int k = 0; k < 6; ++k) xx[k] = x[k];
     branch::Sym6 A;
     branch::eval_fgh(branch::StructView{ &D }, ls, param[26], scale, xx, *f, gg, A, F);
-    for (int a = 0; a < 6; ++a) { g[a] = gg[a]; for (int b = 0; b < 6; ++b) H[6 * a + b] = A.a[tron::tri(a, b)]; }
+    for (int a = 0; a < 6; ++a) { g[a] = gg[a]; for (int b = 0; b < 6; ++b) H[6 * a + b] = A.at(a, b); }
 }
 
 // One generator of the multi-period model (genramp.cuh). param: gen_membuf column (8 doubles; [6] multiplier and
