@@ -29,7 +29,7 @@ __global__ void k_lane(double *out, long long *cyc) {
 #pragma unroll 1
     for (int i = 0; i < N_EV; ++i) {
         branch::eval_fgh(branch::StructView{ &D }, ls, 100.0, 1e-5, x, f, g, A, F);
-        x[2] += 1e-9 * (g[2] + A.a[5]);          // the next point depends on this evaluation
+        x[2] += 1e-9 * (g[2] + A.a22);           // the next point depends on this evaluation
         x[0] -= 1e-12 * f;
     }
     const long long t1 = clk();
@@ -89,14 +89,12 @@ __device__ __forceinline__ void eval_coop4(const branch::Data &D, const double (
     g[0] = scale * (2.0 * As * vi + vj * Ps + 2.0 * vi * ri); g[1] = scale * (2.0 * Bs * vj + vi * Ps + 2.0 * vj * rj);
     g[2] = scale * (gy2 + D.lam[6] + rho6 * dti); g[3] = scale * (-gy2 + D.lam[7] + rho7 * dtj);
     g[4] = scale * m0; g[5] = scale * m1;
-    using tron::tri;
     const double smu = scale * mu;
-    A.a[tri(0, 0)] = scale * H00; A.a[tri(1, 0)] = scale * H01; A.a[tri(1, 1)] = scale * H11;
-    A.a[tri(2, 0)] = scale * H02; A.a[tri(2, 1)] = scale * H12; A.a[tri(2, 2)] = scale * (H22 + rho6);
-    A.a[tri(3, 0)] = -(scale * H02); A.a[tri(3, 1)] = -(scale * H12); A.a[tri(3, 2)] = -(scale * H22); A.a[tri(3, 3)] = scale * (H22 + rho7);
-    A.a[tri(4, 0)] = smu * da0; A.a[tri(4, 1)] = smu * da1; A.a[tri(4, 2)] = smu * da2; A.a[tri(4, 3)] = -(smu * da2); A.a[tri(4, 4)] = smu;
-    A.a[tri(5, 0)] = smu * db0; A.a[tri(5, 1)] = smu * db1; A.a[tri(5, 2)] = smu * db2; A.a[tri(5, 3)] = -(smu * db2);
-    A.a[tri(5, 4)] = 0.0; A.a[tri(5, 5)] = smu;
+    A.a00 = scale * H00; A.a10 = scale * H01; A.a11 = scale * H11;
+    A.a20 = scale * H02; A.a21 = scale * H12; A.a22 = scale * (H22 + rho6);
+    A.a32 = -(scale * H22); A.a33 = scale * (H22 + rho7);
+    A.a40 = smu * da0; A.a41 = smu * da1; A.a42 = smu * da2; A.a44 = smu;
+    A.a50 = smu * db0; A.a51 = smu * db1; A.a52 = smu * db2;
 }
 
 __global__ void k_coop(double *out, long long *cyc, int lanes_on) {
@@ -109,7 +107,7 @@ __global__ void k_coop(double *out, long long *cyc, int lanes_on) {
 #pragma unroll 1
         for (int i = 0; i < N_EV; ++i) {
             eval_coop4(D, ls, 100.0, 1e-5, x, f, g, A);
-            x[2] += 1e-9 * (g[2] + A.a[5]);
+            x[2] += 1e-9 * (g[2] + A.a22);
             x[0] -= 1e-12 * f;
         }
     }
