@@ -10,15 +10,18 @@
 // One lane owns one branch at a time. The objective uses the structure every flow
 // shares, F = a vi^2 + b vj^2 + vi vj P(t), t = ti - tj:
 // gradient and Hessian are assembled in the 3 variables (vi, vj, t) from
-// aggregated flow weights and then expanded to the 6x6 packed matrix, one
-// sincos per evaluation, f/grad/Hessian fused.
+// aggregated flow weights and then expanded to the 6x6 matrix (kept in its 15
+// independent entries, Hess), one sincos per evaluation. The evaluation comes in
+// three parts (flows / f and gradient / Hessian) so that a trial point costs only
+// what its judgement needs (eval_pass).
 //
 // The AL loop and TRON's reverse-communication loop are flattened into a state
 // machine (`Lane`) advanced by three uniform phases per round,
 //     eval_pass(0)  lanes holding a trial point: evaluate, judge, converge, AL update
 //     eval_pass(1)  lanes starting a TRON solve (new branch, next AL iteration, or a
 //                   rejected step): evaluate at the current point
-//     compute()     every live lane: Cauchy point + projected CG -> next trial point
+//     compute()     every live lane: dtron's COMPUTE (Cauchy point + projected CG), taken directly where it runs its
+//                   common course (tron::newton_step) -> next trial point
 // so that the lanes of a warp, each at a different stage of a different branch,
 // execute the same instructions. The kernel (kernels.cuh) refills finished lanes
 // with new branches between the phases; the host test harness drives the very same

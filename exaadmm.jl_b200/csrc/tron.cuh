@@ -16,7 +16,11 @@
 //     the compacted form;
 //   * the reverse-communication protocol is flattened into "compute trial step"
 //     and "judge trial step" so that a warp's lanes, each at a different stage
-//     of its own solve, still execute the same code (branch.cuh).
+//     of its own solve, still execute the same code (branch.cuh);
+//   * "compute trial step" has two forms: the literal algorithm (compute_step: dcauchy, dspcg with dicfs / dtrpcg /
+//     dprsrch) and newton_step, which takes the step directly where the literal algorithm runs its common course
+//     (> 99.9 % of the steps) and declines otherwise (compute_step_auto);
+//   * matrices are read through at(i, j), so a caller can hand in a structured type (branch::Hess).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
